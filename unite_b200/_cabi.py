@@ -1,0 +1,67 @@
+"""ctypes binding of the C ABI in include/unite_b200.h.
+
+This is the only place the shared library is loaded.  It fails loudly (ImportError) when the library has
+not been built — there is no Python/torch fallback for any op on the product path.
+"""
+import ctypes as C
+import os
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libunite_b200.so")
+
+UB_ACT_NONE, UB_ACT_QUICKGELU, UB_ACT_GELU, UB_ACT_DGELU = 0, 1, 2, 3
+
+
+class GemmEpilogue(C.Structure):
+    _fields_ = [
+        ("bias", C.c_void_p),
+        ("residual", C.c_void_p),
+        ("row_scale", C.c_void_p),
+        ("aux_in", C.c_void_p),
+        ("aux_out", C.c_void_p),
+        ("ldr", C.c_int64),
+        ("ld_aux", C.c_int64),
+        ("rows_per_scale", C.c_int32),
+        ("act", C.c_int32),
+        ("out_fp32", C.c_int32),
+        ("accumulate", C.c_int32),
+    ]
+
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"unite_b200: {_LIB_PATH} is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C unite_b200/csrc`). There is no fallback path."
+        )
+    return C.CDLL(_LIB_PATH)
+
+
+lib = _load()
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header.
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+SIGNATURES = {
+    "ub_version": (C.c_int, []),
+    "ub_last_error": (C.c_char_p, []),
+    "ub_sm_count": (C.c_int, []),
+    "ub_gemm_bf16": (C.c_int, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, C.POINTER(GemmEpilogue), _I, _P]),
+}
+
+
+def _bind():
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+
+
+_bind()
+
+
+class UBError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise UBError(f"{what}: {lib.ub_last_error().decode()}")
