@@ -18,7 +18,7 @@ namespace ub {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 struct GemmParams {
   void* C;
@@ -44,6 +44,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);  // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -57,7 +58,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     fence_mbar_init();
   }
@@ -153,28 +154,68 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (as == 0) aphase ^= 1;
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int sp = warp & 3;  // TMEM sub-partition this warp may read
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM sub-partition, each owning half of the tile's columns.  Global operands of the
+    // epilogue are never waited on serially: the bias slice is staged in smem once per tile, residual / aux
+    // rows are prefetched one 32-column chunk ahead of the TMEM load they are combined with.
+    const int sp = warp & 3;            // TMEM sub-partition this warp may read
+    const int half = (warp - 2) >> 2;   // which half of the BN columns
+    const int etid = threadIdx.x - 64;  // 0..255
+    constexpr int CHUNKS = BN / 64;     // 32-column chunks per warp
     int as = 0;
     uint32_t aphase = 0;
     const ub_gemm_epilogue& ep = p.ep;
+    const bool has_res = ep.residual != nullptr;
+    const bool has_aux_in = ep.act == UB_ACT_DGELU;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int tile = w / p.splits;
       const int m0 = (tile / n_tiles) * BM;
       const int n0 = (tile % n_tiles) * BN;
       const int row = m0 + sp * 32 + lane;
       const bool row_ok = row < p.M;
+      float* bias_tile = bias_s + as * BN;
+      if (ep.bias != nullptr) {
+        if (etid < BN) bias_tile[etid] = (n0 + etid < p.N) ? __ldg(ep.bias + n0 + etid) : 0.0f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       float rscale = 1.0f;
       if (ep.row_scale != nullptr && row_ok) rscale = __ldg(ep.row_scale + row / ep.rows_per_scale);
+      const int cbase = n0 + half * (BN / 2);
+      const float* res_row = has_res ? ep.residual + (int64_t)row * ep.ldr : nullptr;
+      const bf16* aux_row = has_aux_in ? reinterpret_cast<const bf16*>(ep.aux_in) + (int64_t)row * ep.ld_aux : nullptr;
+      float4 rn[8];
+      uint4 an[4];
+      auto prefetch = [&](int c) {
+        const int col0 = cbase + c * 32;
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            rn[j] = (row_ok && col0 + j * 4 < p.N) ? *reinterpret_cast<const float4*>(res_row + col0 + j * 4)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (has_aux_in) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            an[j] = (row_ok && col0 + j * 8 < p.N) ? ldg_nc_v4(aux_row + col0 + j * 8) : make_uint4(0, 0, 0, 0);
+        }
+      };
+      prefetch(0);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(sp * 32) << 16) + (uint32_t)(as * BN);
+      const uint32_t t_row = tmem_base + ((uint32_t)(sp * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int col0 = cbase + c * 32;
         if (col0 >= p.N) break;
         uint32_t r[32];
         tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
+        float4 rc[8];
+        uint4 ac[4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rc[j] = rn[j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ac[j] = an[j];
+        if (c + 1 < CHUNKS) prefetch(c + 1);
         tmem_ld_wait();
         if (!row_ok) continue;
 #pragma unroll
@@ -185,8 +226,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
           if (ep.bias != nullptr) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col + 4));
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_tile + (col - n0));
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_tile + (col - n0) + 4);
             v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
             v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
           }
@@ -203,7 +244,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
           } else if (ep.act == UB_ACT_DGELU) {
-            const uint4 pk = ldg_nc_v4(reinterpret_cast<const bf16*>(ep.aux_in) + (int64_t)row * ep.ld_aux + col);
+            const uint4 pk = ac[g];
             const float2 a0 = unpack_bf16x2(pk.x), a1 = unpack_bf16x2(pk.y), a2 = unpack_bf16x2(pk.z),
                          a3 = unpack_bf16x2(pk.w);
             v[0] *= gelu_erf_grad(a0.x); v[1] *= gelu_erf_grad(a0.y);
@@ -215,9 +256,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] *= rscale;
           }
-          if (ep.residual != nullptr) {
-            const float4 r0 = *reinterpret_cast<const float4*>(ep.residual + (int64_t)row * ep.ldr + col);
-            const float4 r1 = *reinterpret_cast<const float4*>(ep.residual + (int64_t)row * ep.ldr + col + 4);
+          if (has_res) {
+            const float4 r0 = rc[g * 2], r1 = rc[g * 2 + 1];
             v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
             v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
           }
@@ -296,7 +336,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
                        cudaStream_t stream) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256 + 2 * BN * 4;
   static bool configured = false;
   auto kern = gemm_kernel<BN, STAGES, A_MN, B_MN>;
   if (!configured) {
