@@ -57,7 +57,7 @@ UB_DEVINL float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 // QuickGELU (teacher, clip.py:29): x * sigmoid(1.702 x)
-UB_DEVINL float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+UB_DEVINL float quick_gelu(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
 
 UB_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
