@@ -57,6 +57,77 @@ UB_API int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* 
                  void* C, int64_t ldc, int M, int N, int K, const ub_gemm_epilogue* ep, int split_k,
                  void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-head self-attention, head_dim 64 (flash-style: the S x S scores never reach HBM).
+ *   qkv bf16 [n_seq*S, 3*H*64] (per row q|k|v, H heads x 64), o bf16 [n_seq*S, H*64], lse fp32 [n_seq,H,S].
+ * Replaces modeling_finetune.py:110-116 (student Attention core) and clip.py:40-52 (nn.MultiheadAttention core);
+ * ub_attn_bwd is their autograd backward (D_ws: fp32 [n_seq,H,S] scratch); ub_cls_attn is clip.py:95-96,183:
+ * out[n_seq, S-1] = head-averaged softmax row of the CLS query (token 0) over the patch keys.
+ * ---------------------------------------------------------------------------------------------- */
+UB_API int ub_attn_fwd(const void* qkv, void* o, float* lse /* may be NULL */, int n_seq, int S, int H, float scale,
+                       void* stream);
+UB_API int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* D_ws, void* dqkv,
+                       int n_seq, int S, int H, float scale, void* stream);
+UB_API int ub_cls_attn(const void* qkv, float* out, int n_seq, int S, int H, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm family (one warp per row, fp32 statistics; D multiple of 128, <= 1024).
+ *   ub_layernorm_fwd   out[r] = LN(x[src_rows ? src_rows[r] : r]) * gamma + beta (+ post_add[post_idx[r]]); bf16 or fp32 out.
+ *                      student norm1/norm2 (modeling_finetune.py:143-150), encoder.norm + gathered clip_pos_embed
+ *                      (modeling_adaptation.py:168,318-320), teacher ln_1/ln_2 (clip.py:55-64), ln_post on gathered
+ *                      visible tokens (clip.py:168 + run_stage1.py:393).
+ *   ub_teacher_embed_ln  CLS/pos assembly + ln_pre (clip.py:150-152): E fp32 [frames*P, D] -> out fp32 [frames*(P+1), D].
+ *   ub_layernorm_bwd   autograd backward of the student LNs fused with the residual-gradient add and the bf16 cast
+ *                      (x DropPath scale) the following GEMMs consume; dgamma/dbeta are ACCUMULATED (red.add).
+ *   ub_dec_tail_fwd/bwd  Linear_Decoder tail (modeling_adaptation.py:205-211): LN(C) then L2 normalise; fwd optionally
+ *                      accumulates the alignment loss sum(2 - 2<out,tgt>) * loss_scale (run_stage1.py:431);
+ *                      bwd takes the upstream gradient as go_scale * go.
+ *   ub_l2norm_rows     x /= ||x|| per row (clip.py:173).
+ * ---------------------------------------------------------------------------------------------- */
+UB_API int ub_layernorm_fwd(const float* x, const int* src_rows, const float* gamma, const float* beta, float eps,
+                            const float* post_add, const int* post_idx, void* out, int out_fp32, int rows, int D,
+                            void* stream);
+UB_API int ub_teacher_embed_ln(const float* E, const float* cls, const float* pos, const float* gamma, const float* beta,
+                               float eps, float* out, int frames, int P, int D, void* stream);
+UB_API int ub_layernorm_bwd(const void* dy, const float* x, const float* gamma, float eps, const float* dx_in,
+                            float* dx_out, void* dxs_out, const float* row_scale, int rows_per_scale, float* dgamma,
+                            float* dbeta, int rows, int D, void* stream);
+UB_API int ub_dec_tail_fwd(const float* y, const float* gamma, const float* beta, float eps, float* out, const float* tgt,
+                           float* loss_acc, float loss_scale, int rows, int D, void* stream);
+UB_API int ub_dec_tail_bwd(const float* y, const float* gamma, const float* beta, float eps, const float* go,
+                           float go_scale, void* dy_out, float* dgamma, float* dbeta, int rows, int D, void* stream);
+UB_API int ub_l2norm_rows(float* x, int rows, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Token movement and the mask sampler.
+ *   ub_patchify     fp32 clip [B,3,T,H,W] -> bf16 im2col rows [B*(T/tub)*(H/16)*(W/16), 3*tub*256]
+ *                   (Conv3d stride==kernel as a GEMM: clip.py:123-128,146; modeling_finetune.py:165-174).
+ *   ub_mask_select  run_stage1.py:379-387 (q != NULL: multinomial w/o replacement == top-n_vis of attn/q, q~Exp(1)
+ *                   supplied by the caller) and utils.py:89-120 get_greedy_masks (q == NULL, k members).  Bit-exact.
+ *                   mask uint8 [k, frames*P] (1 = masked), vis_idx / tea_rows int32 [k, frames/T, T*n_vis].
+ *   ub_gather_rows  out[i,:] = in[(i / rows_per_group) * group_stride_rows + idx[i], :]  (rows_per_group == 0: no base)
+ *                   — the `x[~mask]` gathers of modeling_adaptation.py:153,319 and run_stage1.py:393.
+ *   ub_colsum_bf16  out[n] += sum_m x[m,n]  (bias gradients).
+ *   ub_cast_scale_bf16  out = bf16(x * row_scale[row / rows_per_scale]).
+ * ---------------------------------------------------------------------------------------------- */
+UB_API int ub_patchify(const float* x, void* out, int B, int T, int H, int W, int tubelet, void* stream);
+UB_API int ub_mask_select(const float* attn, const float* q, uint8_t* mask, int* vis_idx, int* tea_rows, int frames,
+                          int P, int T, int k, int n_vis, void* stream);
+UB_API int ub_gather_rows(const void* in, const int* idx, void* out, int64_t n_rows, int64_t row_bytes,
+                          int rows_per_group, int64_t group_stride_rows, void* stream);
+UB_API int ub_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, void* stream);
+UB_API int ub_cast_scale_bf16(const float* x, void* out, const float* row_scale, int rows_per_scale, int64_t rows, int D,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer over the flat parameter arena [decay | no-decay]  (src/optim_factory.py:76-118,162-163; src/utils.py:631-643).
+ * ---------------------------------------------------------------------------------------------- */
+UB_API int ub_sumsq(const float* g, int64_t n, float* out /* accumulated */, void* stream);
+UB_API int ub_adamw(float* p, const float* g, float* m, float* v, void* w_bf16 /* may be NULL */, int64_t n,
+                    int64_t n_decay, float lr, float wd, float beta1, float beta2, float eps, int step, float grad_scale,
+                    void* stream);
+UB_API int ub_cast_bf16(const float* x, void* out, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,23 @@ SIGNATURES = {
     "ub_last_error": (C.c_char_p, []),
     "ub_sm_count": (C.c_int, []),
     "ub_gemm_bf16": (C.c_int, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, C.POINTER(GemmEpilogue), _I, _P]),
+    "ub_attn_fwd": (C.c_int, [_P, _P, _P, _I, _I, _I, _F, _P]),
+    "ub_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "ub_cls_attn": (C.c_int, [_P, _P, _I, _I, _I, _F, _P]),
+    "ub_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P]),
+    "ub_teacher_embed_ln": (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _P]),
+    "ub_layernorm_bwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P]),
+    "ub_dec_tail_fwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _F, _I, _I, _P]),
+    "ub_dec_tail_bwd": (C.c_int, [_P, _P, _P, _F, _P, _F, _P, _P, _P, _I, _I, _P]),
+    "ub_l2norm_rows": (C.c_int, [_P, _I, _I, _P]),
+    "ub_patchify": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "ub_mask_select": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "ub_gather_rows": (C.c_int, [_P, _P, _P, _L, _L, _I, _L, _P]),
+    "ub_colsum_bf16": (C.c_int, [_P, _L, _P, _I, _I, _P]),
+    "ub_cast_scale_bf16": (C.c_int, [_P, _P, _P, _I, _L, _I, _P]),
+    "ub_sumsq": (C.c_int, [_P, _L, _P, _P]),
+    "ub_adamw": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
+    "ub_cast_bf16": (C.c_int, [_P, _P, _L, _P]),
 }
 
 

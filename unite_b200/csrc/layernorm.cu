@@ -1,0 +1,434 @@
+// LayerNorm family (HBM-bound): one warp per row, the row lives in registers, 128-bit coalesced access.
+//
+// Replaces   student  nn.LayerNorm(eps=1e-6): modeling_finetune.py:143-150 (norm1/norm2), modeling_adaptation.py:168
+//                     (shared encoder.norm on the K tapped layers) + :318-320 (gathered clip_pos_embed add),
+//                     Linear_Decoder.norm + L2 normalise (modeling_adaptation.py:203-213), fc_norm (modeling_finetune.py:376)
+//            teacher  fp32 LayerNorm subclass (clip.py:20-26): ln_pre with CLS/pos assembly (:150-152), ln_1/ln_2 (:55-64),
+//                     ln_post on gathered visible tokens (:168)
+// and the autograd backward of the student ones.  Statistics are always fp32; the residual stream is fp32;
+// outputs that feed a GEMM are bf16.  D must be a multiple of 128 and <= 1024.
+#include "common.cuh"
+#include "../../include/unite_b200.h"
+
+namespace ub {
+
+constexpr int LN_MAXV = 8;  // float4 per lane -> D <= 1024
+
+struct RowF {
+  float4 v[LN_MAXV];
+};
+
+UB_DEVINL void row_load_f32(RowF& r, const float* p, int nv, int lane) {
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv) r.v[i] = *reinterpret_cast<const float4*>(p + (i * 32 + lane) * 4);
+}
+UB_DEVINL void row_load_bf16(RowF& r, const bf16* p, int nv, int lane) {
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv) {
+      const uint2 u = *reinterpret_cast<const uint2*>(p + (i * 32 + lane) * 4);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      r.v[i] = make_float4(a.x, a.y, b.x, b.y);
+    }
+}
+UB_DEVINL void row_store_f32(const RowF& r, float* p, int nv, int lane) {
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv) *reinterpret_cast<float4*>(p + (i * 32 + lane) * 4) = r.v[i];
+}
+UB_DEVINL void row_store_bf16(const RowF& r, bf16* p, int nv, int lane) {
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv) {
+      uint2 u;
+      u.x = pack_bf16x2(r.v[i].x, r.v[i].y);
+      u.y = pack_bf16x2(r.v[i].z, r.v[i].w);
+      *reinterpret_cast<uint2*>(p + (i * 32 + lane) * 4) = u;
+    }
+}
+UB_DEVINL float row_sum(const RowF& r, int nv) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv) s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
+  return warp_sum(s);
+}
+UB_DEVINL float row_dot(const RowF& a, const RowF& b, int nv) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv) s += a.v[i].x * b.v[i].x + a.v[i].y * b.v[i].y + a.v[i].z * b.v[i].z + a.v[i].w * b.v[i].w;
+  return warp_sum(s);
+}
+// two-pass mean / rstd (matches torch's fp32 layer_norm to round-off); leaves x centred: x <- x - mean
+UB_DEVINL float row_center_rstd(RowF& x, int nv, int D, float eps) {
+  const float mean = row_sum(x, nv) / (float)D;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+    if (i < nv) {
+      x.v[i].x -= mean; x.v[i].y -= mean; x.v[i].z -= mean; x.v[i].w -= mean;
+      s += x.v[i].x * x.v[i].x + x.v[i].y * x.v[i].y + x.v[i].z * x.v[i].z + x.v[i].w * x.v[i].w;
+    }
+  s = warp_sum(s);
+  return rsqrtf(s / (float)D + eps);
+}
+#define UB_ROW_FOREACH(i, nv) _Pragma("unroll") for (int i = 0; i < LN_MAXV; ++i) if (i < nv)
+
+// ------------------------------------------------------------------------------------------------
+// forward:  out[r] = LN(x[src(r)]) * gamma + beta  (+ post_add[post_idx[r]])
+// ------------------------------------------------------------------------------------------------
+struct LnFwdArgs {
+  const float* x;
+  const int* src_rows;    // optional gather of input rows
+  const float* gamma;
+  const float* beta;
+  const float* post_add;  // optional fp32 table [*, D]
+  const int* post_idx;    // row of post_add per output row
+  void* out;
+  int out_fp32;
+  int rows, D;
+  float eps;
+};
+
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int nv = a.D >> 7;
+  const int wpb = blockDim.x >> 5;
+  RowF g, b;
+  row_load_f32(g, a.gamma, nv, lane);
+  row_load_f32(b, a.beta, nv, lane);
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < a.rows; row += gridDim.x * wpb) {
+    const int64_t src = a.src_rows ? a.src_rows[row] : row;
+    RowF x;
+    row_load_f32(x, a.x + src * a.D, nv, lane);
+    const float rstd = row_center_rstd(x, nv, a.D, a.eps);
+    UB_ROW_FOREACH(i, nv) {
+      x.v[i].x = x.v[i].x * rstd * g.v[i].x + b.v[i].x;
+      x.v[i].y = x.v[i].y * rstd * g.v[i].y + b.v[i].y;
+      x.v[i].z = x.v[i].z * rstd * g.v[i].z + b.v[i].z;
+      x.v[i].w = x.v[i].w * rstd * g.v[i].w + b.v[i].w;
+    }
+    if (a.post_add) {
+      RowF pa;
+      row_load_f32(pa, a.post_add + (int64_t)a.post_idx[row] * a.D, nv, lane);
+      UB_ROW_FOREACH(i, nv) {
+        x.v[i].x += pa.v[i].x; x.v[i].y += pa.v[i].y; x.v[i].z += pa.v[i].z; x.v[i].w += pa.v[i].w;
+      }
+    }
+    if (a.out_fp32) row_store_f32(x, reinterpret_cast<float*>(a.out) + (int64_t)row * a.D, nv, lane);
+    else row_store_bf16(x, reinterpret_cast<bf16*>(a.out) + (int64_t)row * a.D, nv, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// teacher token assembly + ln_pre (clip.py:150-152): row (f, tok):  tok==0 ? cls : E[f*P + tok-1], + pos[tok], LN
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) teacher_embed_ln_kernel(const float* __restrict__ E, const float* __restrict__ cls,
+                                                               const float* __restrict__ pos, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float* __restrict__ out,
+                                                               int frames, int P, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nv = D >> 7;
+  const int wpb = blockDim.x >> 5;
+  const int rows = frames * (P + 1);
+  RowF g, b;
+  row_load_f32(g, gamma, nv, lane);
+  row_load_f32(b, beta, nv, lane);
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const int f = row / (P + 1), tok = row % (P + 1);
+    RowF x, pe;
+    if (tok == 0) row_load_f32(x, cls, nv, lane);
+    else row_load_f32(x, E + ((int64_t)f * P + tok - 1) * D, nv, lane);
+    row_load_f32(pe, pos + (int64_t)tok * D, nv, lane);
+    UB_ROW_FOREACH(i, nv) {
+      x.v[i].x += pe.v[i].x; x.v[i].y += pe.v[i].y; x.v[i].z += pe.v[i].z; x.v[i].w += pe.v[i].w;
+    }
+    const float rstd = row_center_rstd(x, nv, D, eps);
+    UB_ROW_FOREACH(i, nv) {
+      x.v[i].x = x.v[i].x * rstd * g.v[i].x + b.v[i].x;
+      x.v[i].y = x.v[i].y * rstd * g.v[i].y + b.v[i].y;
+      x.v[i].z = x.v[i].z * rstd * g.v[i].z + b.v[i].z;
+      x.v[i].w = x.v[i].w * rstd * g.v[i].w + b.v[i].w;
+    }
+    row_store_f32(x, out + (int64_t)row * D, nv, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward of y = LN(x)*gamma + beta, fused with the residual-stream gradient:
+//   dx_out = (dx_in or 0) + rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat))
+//   dxs_out (bf16, optional) = bf16(dx_out * row_scale)          -- operand of the next dgrad / wgrad GEMMs
+//   dgamma += sum_rows dy*xhat,  dbeta += sum_rows dy            -- red.add into fp32 [D]
+// ------------------------------------------------------------------------------------------------
+struct LnBwdArgs {
+  const bf16* dy;
+  const float* x;
+  const float* gamma;
+  const float* dx_in;       // optional
+  float* dx_out;
+  bf16* dxs_out;            // optional
+  const float* row_scale;   // optional, indexed row / rows_per_scale
+  int rows_per_scale;
+  float* dgamma;
+  float* dbeta;
+  int rows, D;
+  float eps;
+};
+
+// block-wide reduction of per-warp column partials, then one red.add per column per block
+UB_DEVINL void block_col_reduce_atomic(const RowF& part, float* s_buf, float* gdst, int nv, int D) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  row_store_f32(part, s_buf + warp * D, nv, lane);
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += s_buf[w * D + c];
+    atomicAdd(gdst + c, s);
+  }
+}
+
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
+  extern __shared__ float s_red[];  // [warps][D]
+  const int lane = threadIdx.x & 31;
+  const int nv = a.D >> 7;
+  const int wpb = blockDim.x >> 5;
+  RowF g, dgam, dbet;
+  row_load_f32(g, a.gamma, nv, lane);
+  UB_ROW_FOREACH(i, nv) {
+    dgam.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    dbet.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float invD = 1.f / (float)a.D;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < a.rows; row += gridDim.x * wpb) {
+    RowF x, dy;
+    row_load_f32(x, a.x + (int64_t)row * a.D, nv, lane);
+    row_load_bf16(dy, a.dy + (int64_t)row * a.D, nv, lane);
+    const float rstd = row_center_rstd(x, nv, a.D, a.eps);
+    float s1 = 0.f, s2 = 0.f;
+    UB_ROW_FOREACH(i, nv) {
+      // x <- xhat ; accumulate dgamma/dbeta ; dy <- g*dy
+      x.v[i].x *= rstd; x.v[i].y *= rstd; x.v[i].z *= rstd; x.v[i].w *= rstd;
+      dgam.v[i].x += dy.v[i].x * x.v[i].x; dgam.v[i].y += dy.v[i].y * x.v[i].y;
+      dgam.v[i].z += dy.v[i].z * x.v[i].z; dgam.v[i].w += dy.v[i].w * x.v[i].w;
+      dbet.v[i].x += dy.v[i].x; dbet.v[i].y += dy.v[i].y; dbet.v[i].z += dy.v[i].z; dbet.v[i].w += dy.v[i].w;
+      dy.v[i].x *= g.v[i].x; dy.v[i].y *= g.v[i].y; dy.v[i].z *= g.v[i].z; dy.v[i].w *= g.v[i].w;
+      s1 += (dy.v[i].x + dy.v[i].y) + (dy.v[i].z + dy.v[i].w);
+      s2 += dy.v[i].x * x.v[i].x + dy.v[i].y * x.v[i].y + dy.v[i].z * x.v[i].z + dy.v[i].w * x.v[i].w;
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+    RowF dx;
+    if (a.dx_in) row_load_f32(dx, a.dx_in + (int64_t)row * a.D, nv, lane);
+    UB_ROW_FOREACH(i, nv) {
+      if (!a.dx_in) dx.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      dx.v[i].x += rstd * (dy.v[i].x - s1 - x.v[i].x * s2);
+      dx.v[i].y += rstd * (dy.v[i].y - s1 - x.v[i].y * s2);
+      dx.v[i].z += rstd * (dy.v[i].z - s1 - x.v[i].z * s2);
+      dx.v[i].w += rstd * (dy.v[i].w - s1 - x.v[i].w * s2);
+    }
+    row_store_f32(dx, a.dx_out + (int64_t)row * a.D, nv, lane);
+    if (a.dxs_out) {
+      const float sc = a.row_scale ? __ldg(a.row_scale + row / a.rows_per_scale) : 1.0f;
+      UB_ROW_FOREACH(i, nv) { dx.v[i].x *= sc; dx.v[i].y *= sc; dx.v[i].z *= sc; dx.v[i].w *= sc; }
+      row_store_bf16(dx, a.dxs_out + (int64_t)row * a.D, nv, lane);
+    }
+  }
+  block_col_reduce_atomic(dgam, s_red, a.dgamma, nv, a.D);
+  block_col_reduce_atomic(dbet, s_red, a.dbeta, nv, a.D);
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder tail (modeling_adaptation.py:203-213): out = u / ||u||,  u = LN(y)*gamma + beta        (fp32 in/out)
+// optionally also accumulates the alignment loss  sum_rows (2 - 2 <out, tgt>) * loss_scale  (run_stage1.py:431)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dec_tail_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ out,
+                                                           const float* __restrict__ tgt, float* __restrict__ loss_acc,
+                                                           float loss_scale, int rows, int D, float eps) {
+  __shared__ float s_loss[8];
+  const int lane = threadIdx.x & 31;
+  const int nv = D >> 7;
+  const int wpb = blockDim.x >> 5;
+  RowF g, b;
+  row_load_f32(g, gamma, nv, lane);
+  row_load_f32(b, beta, nv, lane);
+  float lacc = 0.f;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    RowF x;
+    row_load_f32(x, y + (int64_t)row * D, nv, lane);
+    const float rstd = row_center_rstd(x, nv, D, eps);
+    UB_ROW_FOREACH(i, nv) {
+      x.v[i].x = x.v[i].x * rstd * g.v[i].x + b.v[i].x;
+      x.v[i].y = x.v[i].y * rstd * g.v[i].y + b.v[i].y;
+      x.v[i].z = x.v[i].z * rstd * g.v[i].z + b.v[i].z;
+      x.v[i].w = x.v[i].w * rstd * g.v[i].w + b.v[i].w;
+    }
+    const float inv = 1.0f / sqrtf(row_dot(x, x, nv));
+    UB_ROW_FOREACH(i, nv) { x.v[i].x *= inv; x.v[i].y *= inv; x.v[i].z *= inv; x.v[i].w *= inv; }
+    row_store_f32(x, out + (int64_t)row * D, nv, lane);
+    if (tgt) {
+      RowF t;
+      row_load_f32(t, tgt + (int64_t)row * D, nv, lane);
+      lacc += 2.0f - 2.0f * row_dot(x, t, nv);
+    }
+  }
+  if (tgt) {
+    if (lane == 0) s_loss[threadIdx.x >> 5] = lacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < wpb; ++w) s += s_loss[w];
+      atomicAdd(loss_acc, s * loss_scale);
+    }
+  }
+}
+
+// backward of the decoder tail.  Upstream gradient wrt `out` is  go_scale * go[row]  (the engine passes
+// go = targets, go_scale = -2/rows_total for the l2 alignment loss; autograd passes grad_output, 1).
+//   du = (go - out*<out,go>) / ||u|| ;  dy = LNbwd(du)  -> bf16 ;  dgamma/dbeta accumulated.
+__global__ void __launch_bounds__(256) dec_tail_bwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, const float* __restrict__ go,
+                                                           float go_scale, bf16* __restrict__ dy_out, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, int rows, int D, float eps) {
+  extern __shared__ float s_red[];
+  const int lane = threadIdx.x & 31;
+  const int nv = D >> 7;
+  const int wpb = blockDim.x >> 5;
+  RowF g, b, dgam, dbet;
+  row_load_f32(g, gamma, nv, lane);
+  row_load_f32(b, beta, nv, lane);
+  UB_ROW_FOREACH(i, nv) {
+    dgam.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    dbet.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float invD = 1.f / (float)D;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    RowF x, u, du;
+    row_load_f32(x, y + (int64_t)row * D, nv, lane);
+    row_load_f32(du, go + (int64_t)row * D, nv, lane);
+    const float rstd = row_center_rstd(x, nv, D, eps);
+    UB_ROW_FOREACH(i, nv) {
+      x.v[i].x *= rstd; x.v[i].y *= rstd; x.v[i].z *= rstd; x.v[i].w *= rstd;   // xhat
+      u.v[i].x = x.v[i].x * g.v[i].x + b.v[i].x; u.v[i].y = x.v[i].y * g.v[i].y + b.v[i].y;
+      u.v[i].z = x.v[i].z * g.v[i].z + b.v[i].z; u.v[i].w = x.v[i].w * g.v[i].w + b.v[i].w;
+    }
+    const float inv = 1.0f / sqrtf(row_dot(u, u, nv));
+    const float ug = row_dot(u, du, nv) * inv * inv;     // <out, go> / ||u||  (still unscaled by go_scale)
+    const float k = go_scale * inv;
+    float s1 = 0.f, s2 = 0.f;
+    UB_ROW_FOREACH(i, nv) {
+      // du <- go_scale * (go - out*<out,go>) / ||u||
+      du.v[i].x = k * (du.v[i].x - u.v[i].x * ug); du.v[i].y = k * (du.v[i].y - u.v[i].y * ug);
+      du.v[i].z = k * (du.v[i].z - u.v[i].z * ug); du.v[i].w = k * (du.v[i].w - u.v[i].w * ug);
+      dgam.v[i].x += du.v[i].x * x.v[i].x; dgam.v[i].y += du.v[i].y * x.v[i].y;
+      dgam.v[i].z += du.v[i].z * x.v[i].z; dgam.v[i].w += du.v[i].w * x.v[i].w;
+      dbet.v[i].x += du.v[i].x; dbet.v[i].y += du.v[i].y; dbet.v[i].z += du.v[i].z; dbet.v[i].w += du.v[i].w;
+      du.v[i].x *= g.v[i].x; du.v[i].y *= g.v[i].y; du.v[i].z *= g.v[i].z; du.v[i].w *= g.v[i].w;
+      s1 += (du.v[i].x + du.v[i].y) + (du.v[i].z + du.v[i].w);
+      s2 += du.v[i].x * x.v[i].x + du.v[i].y * x.v[i].y + du.v[i].z * x.v[i].z + du.v[i].w * x.v[i].w;
+    }
+    s1 = warp_sum(s1) * invD;
+    s2 = warp_sum(s2) * invD;
+    UB_ROW_FOREACH(i, nv) {
+      du.v[i].x = rstd * (du.v[i].x - s1 - x.v[i].x * s2); du.v[i].y = rstd * (du.v[i].y - s1 - x.v[i].y * s2);
+      du.v[i].z = rstd * (du.v[i].z - s1 - x.v[i].z * s2); du.v[i].w = rstd * (du.v[i].w - s1 - x.v[i].w * s2);
+    }
+    row_store_bf16(du, dy_out + (int64_t)row * D, nv, lane);
+  }
+  block_col_reduce_atomic(dgam, s_red, dgamma, nv, D);
+  block_col_reduce_atomic(dbet, s_red, dbeta, nv, D);
+}
+
+// x[row] /= ||x[row]||   (teacher targets, clip.py:173)
+__global__ void __launch_bounds__(256) l2norm_rows_kernel(float* __restrict__ x, int rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int nv = D >> 7;
+  const int wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    RowF v;
+    row_load_f32(v, x + (int64_t)row * D, nv, lane);
+    const float inv = 1.0f / sqrtf(row_dot(v, v, nv));
+    UB_ROW_FOREACH(i, nv) { v.v[i].x *= inv; v.v[i].y *= inv; v.v[i].z *= inv; v.v[i].w *= inv; }
+    row_store_f32(v, x + (int64_t)row * D, nv, lane);
+  }
+}
+
+static int ln_grid(int rows) {
+  const int want = (rows + 7) / 8;
+  const int cap = sm_count() * 8;
+  return want < cap ? want : cap;
+}
+static int ln_bwd_grid(int rows) {
+  const int want = (rows + 7) / 8;
+  const int cap = sm_count() * 2;
+  return want < cap ? want : cap;
+}
+static int check_D(int D, const char* who) {
+  UB_REQUIRE(D % 128 == 0 && D >= 128 && D <= 128 * LN_MAXV, "%s: feature dim must be a multiple of 128 in [128,1024] (D=%d)", who, D);
+  return 0;
+}
+
+}  // namespace ub
+
+using namespace ub;
+
+extern "C" int ub_layernorm_fwd(const float* x, const int* src_rows, const float* gamma, const float* beta, float eps,
+                                const float* post_add, const int* post_idx, void* out, int out_fp32, int rows, int D,
+                                void* stream) {
+  UB_REQUIRE(x && gamma && beta && out, "layernorm_fwd: null pointer");
+  UB_REQUIRE(rows > 0, "layernorm_fwd: rows=%d", rows);
+  UB_REQUIRE((post_add == nullptr) == (post_idx == nullptr), "layernorm_fwd: post_add and post_idx go together");
+  if (check_D(D, "layernorm_fwd")) return 1;
+  LnFwdArgs a{x, src_rows, gamma, beta, post_add, post_idx, out, out_fp32, rows, D, eps};
+  ln_fwd_kernel<<<ln_grid(rows), 256, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("ln_fwd_kernel");
+}
+
+extern "C" int ub_teacher_embed_ln(const float* E, const float* cls, const float* pos, const float* gamma,
+                                   const float* beta, float eps, float* out, int frames, int P, int D, void* stream) {
+  UB_REQUIRE(E && cls && pos && gamma && beta && out, "teacher_embed_ln: null pointer");
+  if (check_D(D, "teacher_embed_ln")) return 1;
+  teacher_embed_ln_kernel<<<ln_grid(frames * (P + 1)), 256, 0, (cudaStream_t)stream>>>(E, cls, pos, gamma, beta, out, frames, P,
+                                                                                        D, eps);
+  return check_launch("teacher_embed_ln_kernel");
+}
+
+extern "C" int ub_layernorm_bwd(const void* dy, const float* x, const float* gamma, float eps, const float* dx_in,
+                                float* dx_out, void* dxs_out, const float* row_scale, int rows_per_scale, float* dgamma,
+                                float* dbeta, int rows, int D, void* stream) {
+  UB_REQUIRE(dy && x && gamma && dx_out && dgamma && dbeta, "layernorm_bwd: null pointer");
+  UB_REQUIRE(row_scale == nullptr || rows_per_scale > 0, "layernorm_bwd: rows_per_scale must be > 0");
+  if (check_D(D, "layernorm_bwd")) return 1;
+  LnBwdArgs a{(const bf16*)dy, x, gamma, dx_in, dx_out, (bf16*)dxs_out, row_scale, rows_per_scale, dgamma, dbeta, rows, D, eps};
+  ln_bwd_kernel<<<ln_bwd_grid(rows), 256, 8 * D * sizeof(float), (cudaStream_t)stream>>>(a);
+  return check_launch("ln_bwd_kernel");
+}
+
+extern "C" int ub_dec_tail_fwd(const float* y, const float* gamma, const float* beta, float eps, float* out,
+                               const float* tgt, float* loss_acc, float loss_scale, int rows, int D, void* stream) {
+  UB_REQUIRE(y && gamma && beta && out, "dec_tail_fwd: null pointer");
+  UB_REQUIRE((tgt == nullptr) || (loss_acc != nullptr), "dec_tail_fwd: tgt needs loss_acc");
+  if (check_D(D, "dec_tail_fwd")) return 1;
+  dec_tail_fwd_kernel<<<ln_grid(rows), 256, 0, (cudaStream_t)stream>>>(y, gamma, beta, out, tgt, loss_acc, loss_scale, rows, D,
+                                                                      eps);
+  return check_launch("dec_tail_fwd_kernel");
+}
+
+extern "C" int ub_dec_tail_bwd(const float* y, const float* gamma, const float* beta, float eps, const float* go,
+                               float go_scale, void* dy_out, float* dgamma, float* dbeta, int rows, int D, void* stream) {
+  UB_REQUIRE(y && gamma && beta && go && dy_out && dgamma && dbeta, "dec_tail_bwd: null pointer");
+  if (check_D(D, "dec_tail_bwd")) return 1;
+  dec_tail_bwd_kernel<<<ln_bwd_grid(rows), 256, 8 * D * sizeof(float), (cudaStream_t)stream>>>(
+      y, gamma, beta, go, go_scale, (bf16*)dy_out, dgamma, dbeta, rows, D, eps);
+  return check_launch("dec_tail_bwd_kernel");
+}
+
+extern "C" int ub_l2norm_rows(float* x, int rows, int D, void* stream) {
+  UB_REQUIRE(x != nullptr && rows > 0, "l2norm_rows: bad arguments");
+  if (check_D(D, "l2norm_rows")) return 1;
+  l2norm_rows_kernel<<<ln_grid(rows), 256, 0, (cudaStream_t)stream>>>(x, rows, D);
+  return check_launch("l2norm_rows_kernel");
+}

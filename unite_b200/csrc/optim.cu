@@ -1,0 +1,105 @@
+// Fused multi-tensor AdamW over the flat parameter arena (+ global grad-norm, + bf16 weight refresh).
+//
+// Replaces   src/optim_factory.py:162-163 (torch.optim.AdamW over two param groups: decay / no-decay,
+//            optim_factory.py:76-118), src/utils.py:631-643 (get_grad_norm_: ~150 per-tensor norm kernels) and
+//            the bf16 re-cast of the weights every GEMM of the next step consumes.
+// All student parameters live in ONE fp32 buffer laid out [decay params | no-decay params]; gradients,
+// exp_avg, exp_avg_sq are parallel buffers; `w_bf16` is the bf16 shadow the GEMMs read.
+#include "common.cuh"
+#include "../../include/unite_b200.h"
+
+namespace ub {
+
+// sum of squares of a flat fp32 buffer, accumulated into out[0] with one red.add per block
+__global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ g, long n4, float* __restrict__ out) {
+  __shared__ float s_part[8];
+  float acc = 0.f;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = g[i];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += s_part[w];
+    atomicAdd(out, s);
+  }
+}
+
+// torch.optim.AdamW semantics (decoupled decay):  p *= 1 - lr*wd;  m,v EMA;  p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+// g is multiplied by grad_scale first (1/world_size when the all-reduce summed, or a clip coefficient).
+__global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                                    float4* __restrict__ v, uint2* __restrict__ w_bf16, long n4, long n4_decay,
+                                                    float lr, float wd, float beta1, float beta2, float eps, float bc1,
+                                                    float bc2_sqrt, float grad_scale) {
+  const float step_size = lr / bc1;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    const float decay = (i < n4_decay) ? (1.0f - lr * wd) : 1.0f;
+#define UB_ADAM_ONE(c)                                               \
+  {                                                                  \
+    const float gr = gg.c * grad_scale;                              \
+    pp.c *= decay;                                                   \
+    mm.c = beta1 * mm.c + (1.0f - beta1) * gr;                       \
+    vv.c = beta2 * vv.c + (1.0f - beta2) * gr * gr;                  \
+    pp.c -= step_size * (mm.c / (sqrtf(vv.c) / bc2_sqrt + eps));     \
+  }
+    UB_ADAM_ONE(x) UB_ADAM_ONE(y) UB_ADAM_ONE(z) UB_ADAM_ONE(w)
+#undef UB_ADAM_ONE
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    if (w_bf16) {
+      uint2 o;
+      o.x = pack_bf16x2(pp.x, pp.y);
+      o.y = pack_bf16x2(pp.z, pp.w);
+      w_bf16[i] = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ out, long n4) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    out[i] = o;
+  }
+}
+
+static int flat_grid4(long n4) {
+  long want = (n4 + 255) / 256;
+  const long cap = (long)sm_count() * 8;
+  return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+}  // namespace ub
+
+using namespace ub;
+
+extern "C" int ub_sumsq(const float* g, int64_t n, float* out, void* stream) {
+  UB_REQUIRE(g && out && n > 0 && n % 4 == 0, "sumsq: n=%lld must be a positive multiple of 4", (long long)n);
+  sumsq_kernel<<<flat_grid4(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)g, n / 4, out);
+  return check_launch("sumsq_kernel");
+}
+
+extern "C" int ub_adamw(float* p, const float* g, float* m, float* v, void* w_bf16, int64_t n, int64_t n_decay, float lr,
+                        float wd, float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+  UB_REQUIRE(p && g && m && v, "adamw: null pointer");
+  UB_REQUIRE(n > 0 && n % 4 == 0 && n_decay % 4 == 0 && n_decay >= 0 && n_decay <= n,
+             "adamw: n=%lld and n_decay=%lld must be multiples of 4", (long long)n, (long long)n_decay);
+  UB_REQUIRE(step >= 1, "adamw: step must be >= 1");
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2 = 1.0f - powf(beta2, (float)step);
+  adamw_kernel<<<flat_grid4(n / 4), 256, 0, (cudaStream_t)stream>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v,
+                                                                   (uint2*)w_bf16, n / 4, n_decay / 4, lr, wd, beta1, beta2, eps,
+                                                                   bc1, sqrtf(bc2), grad_scale);
+  return check_launch("adamw_kernel");
+}
+
+extern "C" int ub_cast_bf16(const float* x, void* out, int64_t n, void* stream) {
+  UB_REQUIRE(x && out && n > 0 && n % 4 == 0, "cast_bf16: n=%lld must be a positive multiple of 4", (long long)n);
+  cast_bf16_kernel<<<flat_grid4(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)out, n / 4);
+  return check_launch("cast_bf16_kernel");
+}

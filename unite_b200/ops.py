@@ -1,0 +1,177 @@
+"""Typed torch-tensor front end of the C ABI (include/unite_b200.h).
+
+Every function here checks dtype / device / contiguity, takes the raw pointers and the CURRENT torch CUDA stream
+and calls straight into libunite_b200.so.  torch is used for memory and streams only — there is no torch
+implementation of any op behind these functions, and no fallback.
+"""
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _cabi
+from ._cabi import lib, check, GemmEpilogue, UB_ACT_NONE, UB_ACT_QUICKGELU, UB_ACT_GELU, UB_ACT_DGELU  # noqa: F401
+
+BF16, F32, I32, U8 = torch.bfloat16, torch.float32, torch.int32, torch.uint8
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor], dtype=None, what="tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _cabi.UBError(f"{what}: expected a CUDA tensor (unite_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise _cabi.UBError(f"{what}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _cabi.UBError(f"{what}: expected a contiguous tensor, got strides {t.stride()}")
+    return t.data_ptr()
+
+
+def _p2d(t: torch.Tensor, dtype, what):
+    """2-D row-major view with arbitrary leading dimension."""
+    if not t.is_cuda or t.dtype != dtype or t.dim() != 2 or t.stride(1) != 1:
+        raise _cabi.UBError(f"{what}: expected a 2-D row-major CUDA {dtype} tensor, got {t.dtype} {tuple(t.shape)} {t.stride()}")
+    return t.data_ptr(), t.stride(0)
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=False, bias=None, residual=None,
+         row_scale=None, rows_per_scale=0, act=UB_ACT_NONE, aux_in=None, aux_out=None, accumulate=False, split_k=1):
+    """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).  a_t / b_t: the operand is stored transposed ([K,M] / [K,N])."""
+    pa, lda = _p2d(a, BF16, "gemm A")
+    pb, ldb = _p2d(b, BF16, "gemm B")
+    if out.dtype not in (BF16, F32):
+        raise _cabi.UBError("gemm out: bf16 or fp32 expected")
+    pc, ldc = _p2d(out, out.dtype, "gemm C")
+    M, N = out.shape
+    K = a.shape[0] if a_t else a.shape[1]
+    am, bn = (a.shape[1] if a_t else a.shape[0]), (b.shape[1] if b_t else b.shape[0])
+    bk = b.shape[0] if b_t else b.shape[1]
+    if am != M or bn != N or bk != K:
+        raise _cabi.UBError(f"gemm: shape mismatch A{tuple(a.shape)} a_t={a_t} B{tuple(b.shape)} b_t={b_t} C{tuple(out.shape)}")
+    ep = GemmEpilogue()
+    if bias is not None:
+        if bias.numel() != N:
+            raise _cabi.UBError("gemm bias: wrong length")
+        ep.bias = _p(bias, F32, "gemm bias")
+    if residual is not None:
+        pr, ldr = _p2d(residual, F32, "gemm residual")
+        if tuple(residual.shape) != (M, N):
+            raise _cabi.UBError("gemm residual: wrong shape")
+        ep.residual, ep.ldr = pr, ldr
+    if row_scale is not None:
+        ep.row_scale = _p(row_scale, F32, "gemm row_scale")
+        ep.rows_per_scale = rows_per_scale
+    if aux_in is not None:
+        px, ldx = _p2d(aux_in, BF16, "gemm aux_in")
+        ep.aux_in, ep.ld_aux = px, ldx
+    if aux_out is not None:
+        px, ldx = _p2d(aux_out, BF16, "gemm aux_out")
+        ep.aux_out, ep.ld_aux = px, ldx
+    ep.act = act
+    ep.out_fp32 = 1 if out.dtype == F32 else 0
+    ep.accumulate = 1 if accumulate else 0
+    check(lib.ub_gemm_bf16(pa, lda, int(a_t), pb, ldb, int(b_t), pc, ldc, M, N, K, C.byref(ep), split_k, _stream()), "ub_gemm_bf16")
+    return out
+
+
+def attn_fwd(qkv, o, lse, n_seq, S, H, scale):
+    check(lib.ub_attn_fwd(_p(qkv, BF16, "qkv"), _p(o, BF16, "o"), _p(lse, F32, "lse"), n_seq, S, H, scale, _stream()), "ub_attn_fwd")
+
+
+def attn_bwd(qkv, o, d_o, lse, d_ws, dqkv, n_seq, S, H, scale):
+    check(lib.ub_attn_bwd(_p(qkv, BF16, "qkv"), _p(o, BF16, "o"), _p(d_o, BF16, "d_o"), _p(lse, F32, "lse"),
+                          _p(d_ws, F32, "D_ws"), _p(dqkv, BF16, "dqkv"), n_seq, S, H, scale, _stream()), "ub_attn_bwd")
+
+
+def cls_attn(qkv, out, n_seq, S, H, scale):
+    check(lib.ub_cls_attn(_p(qkv, BF16, "qkv"), _p(out, F32, "attn"), n_seq, S, H, scale, _stream()), "ub_cls_attn")
+
+
+def layernorm_fwd(x, gamma, beta, eps, out, *, src_rows=None, post_add=None, post_idx=None):
+    rows, D = out.shape
+    check(lib.ub_layernorm_fwd(_p(x, F32, "ln x"), _p(src_rows, I32, "src_rows"), _p(gamma, F32, "gamma"), _p(beta, F32, "beta"),
+                               eps, _p(post_add, F32, "post_add"), _p(post_idx, I32, "post_idx"), _p(out, None, "ln out"),
+                               1 if out.dtype == F32 else 0, rows, D, _stream()), "ub_layernorm_fwd")
+    return out
+
+
+def teacher_embed_ln(E, cls, pos, gamma, beta, eps, out, frames, P, D):
+    check(lib.ub_teacher_embed_ln(_p(E, F32, "E"), _p(cls, F32, "cls"), _p(pos, F32, "pos"), _p(gamma, F32, "gamma"),
+                                  _p(beta, F32, "beta"), eps, _p(out, F32, "out"), frames, P, D, _stream()), "ub_teacher_embed_ln")
+
+
+def layernorm_bwd(dy, x, gamma, eps, dx_in, dx_out, dxs_out, row_scale, rows_per_scale, dgamma, dbeta):
+    rows, D = x.shape
+    check(lib.ub_layernorm_bwd(_p(dy, BF16, "dy"), _p(x, F32, "x"), _p(gamma, F32, "gamma"), eps, _p(dx_in, F32, "dx_in"),
+                               _p(dx_out, F32, "dx_out"), _p(dxs_out, BF16, "dxs_out"), _p(row_scale, F32, "row_scale"),
+                               rows_per_scale, _p(dgamma, F32, "dgamma"), _p(dbeta, F32, "dbeta"), rows, D, _stream()),
+          "ub_layernorm_bwd")
+
+
+def dec_tail_fwd(y, gamma, beta, eps, out, tgt=None, loss_acc=None, loss_scale=0.0):
+    rows, D = y.shape
+    check(lib.ub_dec_tail_fwd(_p(y, F32, "y"), _p(gamma, F32, "gamma"), _p(beta, F32, "beta"), eps, _p(out, F32, "out"),
+                              _p(tgt, F32, "tgt"), _p(loss_acc, F32, "loss_acc"), loss_scale, rows, D, _stream()), "ub_dec_tail_fwd")
+
+
+def dec_tail_bwd(y, gamma, beta, eps, go, go_scale, dy_out, dgamma, dbeta):
+    rows, D = y.shape
+    check(lib.ub_dec_tail_bwd(_p(y, F32, "y"), _p(gamma, F32, "gamma"), _p(beta, F32, "beta"), eps, _p(go, F32, "go"), go_scale,
+                              _p(dy_out, BF16, "dy_out"), _p(dgamma, F32, "dgamma"), _p(dbeta, F32, "dbeta"), rows, D, _stream()),
+          "ub_dec_tail_bwd")
+
+
+def l2norm_rows(x):
+    rows, D = x.shape
+    check(lib.ub_l2norm_rows(_p(x, F32, "x"), rows, D, _stream()), "ub_l2norm_rows")
+
+
+def patchify(x, out, tubelet):
+    B, Cc, T, H, W = x.shape
+    if Cc != 3:
+        raise _cabi.UBError("patchify: 3 input channels expected")
+    check(lib.ub_patchify(_p(x, F32, "videos"), _p(out, BF16, "patches"), B, T, H, W, tubelet, _stream()), "ub_patchify")
+    return out
+
+
+def mask_select(attn, q, mask, vis_idx, tea_rows, T, k, n_vis):
+    frames, P = attn.shape
+    check(lib.ub_mask_select(_p(attn, F32, "attn"), _p(q, F32, "q"), _p(mask, U8, "mask"), _p(vis_idx, I32, "vis_idx"),
+                             _p(tea_rows, I32, "tea_rows"), frames, P, T, k, n_vis, _stream()), "ub_mask_select")
+
+
+def gather_rows(src, idx, out, rows_per_group=0, group_stride_rows=0):
+    n_rows = idx.numel()
+    row_bytes = out.shape[-1] * out.element_size()
+    check(lib.ub_gather_rows(_p(src, out.dtype, "gather src"), _p(idx, I32, "gather idx"), _p(out, None, "gather out"), n_rows,
+                             row_bytes, rows_per_group, group_stride_rows, _stream()), "ub_gather_rows")
+    return out
+
+
+def colsum_bf16(x, out):
+    px, ld = _p2d(x, BF16, "colsum x")
+    M, N = x.shape
+    check(lib.ub_colsum_bf16(px, ld, _p(out, F32, "colsum out"), M, N, _stream()), "ub_colsum_bf16")
+
+
+def cast_scale_bf16(x, out, row_scale=None, rows_per_scale=0):
+    rows, D = x.shape
+    check(lib.ub_cast_scale_bf16(_p(x, F32, "x"), _p(out, BF16, "out"), _p(row_scale, F32, "row_scale"), rows_per_scale, rows, D,
+                                 _stream()), "ub_cast_scale_bf16")
+
+
+def sumsq(g, out):
+    check(lib.ub_sumsq(_p(g, F32, "g"), g.numel(), _p(out, F32, "out"), _stream()), "ub_sumsq")
+
+
+def adamw(p, g, m, v, w16, n_decay, lr, wd, beta1, beta2, eps, step, grad_scale=1.0):
+    check(lib.ub_adamw(_p(p, F32, "p"), _p(g, F32, "g"), _p(m, F32, "m"), _p(v, F32, "v"), _p(w16, BF16, "w16"), p.numel(), n_decay,
+                       lr, wd, beta1, beta2, eps, step, grad_scale, _stream()), "ub_adamw")
+
+
+def cast_bf16(x, out):
+    check(lib.ub_cast_bf16(_p(x, F32, "x"), _p(out, BF16, "out"), x.numel(), _stream()), "ub_cast_bf16")
