@@ -115,8 +115,8 @@ def close(a, b, tol, what):
 
 def tiny_cfgs():
     scfg = O.StudentCfg(embed_dim=128, depth=3, num_heads=2, num_frames=4, tubelet_size=1, img_size=64,
-                        patch_size=16, return_layers=(1, 2), clip_output_dim=64, num_classes=12)
-    tcfg = O.TeacherCfg(width=128, layers=3, heads=2, output_dim=64, input_resolution=64, patch_size=16,
+                        patch_size=16, return_layers=(1, 2), clip_output_dim=128, num_classes=12)
+    tcfg = O.TeacherCfg(width=128, layers=3, heads=2, output_dim=128, input_resolution=64, patch_size=16,
                         kernel_size=1, return_layers=(1, 2))
     return scfg, tcfg
 
@@ -256,7 +256,7 @@ def main():
         student_shapes={k: tuple(v.shape) for k, v in ssd.items()}, teacher_shapes={k: tuple(v.shape) for k, v in tsd.items()},
         vit_shapes={k: tuple(v.shape) for k, v in vsd.items()}, seeds=dict(student=0, teacher=1, vit=2),
         videos=videos, q=q, labels=labels,
-        attn=ref["attn"], mask=ref["mask"], targets=ref["targets"], outputs=ref["outputs"], loss=ref["loss"],
+        attn=ref["attn"].clone(), mask=ref["mask"], targets=ref["targets"].clone(), outputs=ref["outputs"].clone(), loss=ref["loss"].clone(),
         grads={k: v for k, v in ref["grads"].items() if k in GRAD_KEYS_STAGE1},
         grad_norms={k: v.norm() for k, v in ref["grads"].items()},
         x_vis=xv_ref, stage2_logits=logits_ref.detach(), stage2_loss=loss2_ref.detach(),
@@ -287,7 +287,7 @@ def main():
     print(f"full ViT-B/16 stage-1 (B=1): oracle == reference (worst grad err {worstF:.2e}); "
           f"loss {refF['loss']:.6f}; student params {n_params}; teacher params {n_params_t}")
     torch.save(dict(
-        student_params=n_params, teacher_params=n_params_t, loss=refF["loss"], attn=refF["attn"],
+        student_params=n_params, teacher_params=n_params_t, loss=refF["loss"].clone(), attn=refF["attn"].clone(),
         attn_rowsum=refF["attn"].sum(-1), n_visible=int((~refF["mask"]).sum()), mask=refF["mask"], q=qF,
         outputs_sample=refF["outputs"][:, 0, :4, :8].clone(), targets_sample=refF["targets"][:, 0, :4, :8].clone(),
         seeds=dict(student=0, teacher=1, inputs=11),

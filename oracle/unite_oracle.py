@@ -206,7 +206,8 @@ def visible_indices(mask: Tensor) -> Tensor:
 # --------------------------------------------------------------------------------------------------
 def student_block(sd: SD, p: str, x: Tensor, heads: int, eps: float, keep_scale: Optional[Tensor] = None) -> Tensor:
     """Block.forward without layer-scale (modeling_finetune.py:143-146) = Attention.forward (:100-119) +
-    Mlp.forward (:66-73).  keep_scale [B] = DropPath factor floor(keep+u)/keep (timm 0.4.12 drop_path) or None."""
+    Mlp.forward (:66-73).  keep_scale [2,B] = DropPath factors floor(keep+u)/keep (timm 0.4.12 drop_path) of the
+    attention branch and of the MLP branch (two independent draws per block, :145-146), or None."""
     B, N, D = x.shape
     d = D // heads
     y = _ln(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps)
@@ -217,13 +218,13 @@ def student_block(sd: SD, p: str, x: Tensor, heads: int, eps: float, keep_scale:
     y = (a @ v).transpose(1, 2).reshape(B, N, D)
     y = F.linear(y, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"])
     if keep_scale is not None:
-        y = y * keep_scale.view(B, 1, 1)
+        y = y * keep_scale[0].view(B, 1, 1)
     x = x + y
     y = _ln(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps)
     y = F.gelu(F.linear(y, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]))
     y = F.linear(y, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
     if keep_scale is not None:
-        y = y * keep_scale.view(B, 1, 1)
+        y = y * keep_scale[1].view(B, 1, 1)
     return x + y
 
 
@@ -232,7 +233,7 @@ def student_forward(sd: SD, x: Tensor, mask: Tensor, cfg: StudentCfg, clip_only:
     """AdaptationVisionTransformer.forward (modeling_adaptation.py:304-334) over
     AdaptationVisionTransformerEncoder.forward_features (:131-169), no CLS token, sinusoid pos-embed.
 
-    mask bool [B, N] (True = masked).  keep_scales [depth, B] optional DropPath factors.
+    mask bool [B, N] (True = masked).  keep_scales [depth, 2, B] optional DropPath factors.
     Returns x_clip [K,B,N_vis,C_out] if clip_only else (x_vis_normed [B,N_vis,D], x_clip).
     """
     B = x.shape[0]

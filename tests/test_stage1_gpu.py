@@ -1,0 +1,147 @@
+"""Stage-1 parity on the GPU: unite_b200 (CUDA kernels through the C ABI) vs the CPU oracle / golden fixtures.
+
+Tolerances (BASELINE.json north_star): mask and gather indices bit-exact; per-token features within 1e-2
+relative (bf16 operands vs the fp32 reference); loss within 1e-3 relative.  Gradients (our addition, SURVEY.md
+§8(c)): per-parameter cosine >= 0.999 and relative L2 <= 2e-2 on the large tensors.
+"""
+import pytest
+import torch
+
+from tests.util import (build_student, build_teacher, cosine, load_golden, oracle_cfgs, per_token_rel, rel_l2, seeded_states)
+
+pytestmark = pytest.mark.gpu
+FEAT_TOL, LOSS_TOL = 1e-2, 1e-3
+
+
+def _models(scfg, tcfg, ssd, tsd):
+    student = build_student(scfg)
+    teacher = build_teacher(tcfg)
+    student.load_state_dict(ssd, strict=True)
+    teacher.load_state_dict(tsd, strict=True)
+    return student.cuda().train(), teacher.cuda().eval()
+
+
+def _check_step(engine, ref, videos, q, big_grad_only=False):
+    loss = engine.forward_backward(videos.cuda(), q.cuda(), attn_override=ref["attn"].cuda().contiguous())
+    torch.cuda.synchronize()
+    last = engine.last
+    # teacher attention (fp) and the mask it implies given the ORACLE's attn (bit-exact)
+    assert rel_l2(last["attn"], ref["attn"]) < FEAT_TOL
+    assert torch.equal(last["mask"].cpu(), ref["mask"]), "mask differs from the reference"
+    from oracle.unite_oracle import visible_indices
+    assert torch.equal(last["vis_idx"].cpu().long(), visible_indices(ref["mask"])), "visible index list differs"
+    K, B, Nv, C = ref["targets"].shape
+    t_err = per_token_rel(last["targets"].view(K, B, Nv, C), ref["targets"])
+    o_err = per_token_rel(last["outputs"], ref["outputs"])
+    print(f"targets per-token rel: mean {t_err.mean():.2e} max {t_err.max():.2e}; outputs: mean {o_err.mean():.2e} max {o_err.max():.2e}")
+    assert t_err.max() < FEAT_TOL, f"teacher target features off by {t_err.max():.3e}"
+    assert o_err.max() < FEAT_TOL, f"student output features off by {o_err.max():.3e}"
+    l_rel = abs(loss.item() - ref["loss"].item()) / abs(ref["loss"].item())
+    print(f"loss {loss.item():.6f} vs {ref['loss'].item():.6f} (rel {l_rel:.2e})")
+    assert l_rel < LOSS_TOL
+    arena = engine.core.arena
+    worst_cos, worst_rel = 1.0, 0.0
+    for k, g_ref in ref["grads"].items():
+        g = arena.g32(k)
+        if big_grad_only and g_ref.numel() < 4096:
+            continue
+        c, r = cosine(g, g_ref), rel_l2(g, g_ref)
+        worst_cos, worst_rel = min(worst_cos, c), max(worst_rel, r)
+        assert c >= 0.999, f"grad {k}: cosine {c:.5f}"
+        assert r <= 2e-2, f"grad {k}: rel L2 {r:.3e}"
+    print(f"grads: worst cosine {worst_cos:.6f}, worst rel L2 {worst_rel:.2e}")
+
+
+def test_tiny_stage1_against_golden_fixture():
+    from unite_b200.engine import Stage1Engine
+    fix = load_golden("tiny_stage12.pt")
+    scfg, tcfg = oracle_cfgs(fix)
+    ssd, tsd, _ = seeded_states(fix)
+    student, teacher = _models(scfg, tcfg, ssd, tsd)
+    eng = Stage1Engine(student, teacher, mask_ratio=fix["cfg"]["mask_ratio"])
+    ref = dict(attn=fix["attn"], mask=fix["mask"], targets=fix["targets"], outputs=fix["outputs"], loss=fix["loss"], grads=fix["grads"])
+    _check_step(eng, ref, fix["videos"], fix["q"])
+    for k, n in fix["grad_norms"].items():
+        got = eng.core.arena.g32(k).norm().item()
+        assert abs(got - n.item()) <= 3e-2 * n.item() + 1e-6, f"|grad {k}| = {got} vs {n.item()}"
+
+
+def test_full_vitb16_stage1_against_oracle():
+    """ViT-B/16 student + CLIP-B/16 teacher, 8x224^2, B=2: the CUDA step against the oracle run here on the CPU."""
+    from oracle import unite_oracle as O
+    from oracle.weights import seeded_state
+    from unite_b200.engine import Stage1Engine
+    scfg, tcfg = O.StudentCfg(), O.TeacherCfg()
+    student, teacher = build_student(scfg), build_teacher(tcfg)
+    ssd = seeded_state({k: tuple(v.shape) for k, v in student.state_dict().items()}, 0)
+    tsd = seeded_state({k: tuple(v.shape) for k, v in teacher.state_dict().items()}, 1)
+    student.load_state_dict(ssd); teacher.load_state_dict(tsd)
+    g = torch.Generator().manual_seed(21)
+    B = 2
+    videos = torch.randn(B, 3, 8, 224, 224, generator=g)
+    q = torch.empty(B * 8, 196).exponential_(1, generator=g)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = O.stage1_step(ssd, tsd, videos, q, scfg, tcfg, mask_ratio=0.8)
+    assert ref["vis_idx"].shape == (B, 320)
+    eng = Stage1Engine(student.cuda().train(), teacher.cuda().eval(), mask_ratio=0.8)
+    _check_step(eng, ref, videos, q, big_grad_only=True)
+
+
+def test_module_api_matches_engine_and_autograd_accumulates():
+    """The reference-facing call `model(videos, mask, clip_only=True)` + loss.backward() gives the same numbers as
+    the fused engine, and a second backward accumulates into .grad like torch does."""
+    from unite_b200.engine import Stage1Engine
+    fix = load_golden("tiny_stage12.pt")
+    scfg, tcfg = oracle_cfgs(fix)
+    ssd, tsd, _ = seeded_states(fix)
+    student, teacher = _models(scfg, tcfg, ssd, tsd)
+    videos, mask = fix["videos"].cuda(), fix["mask"].cuda()
+    with torch.no_grad():
+        feat, attn = teacher(videos)
+    K, C = feat.shape[0], feat.shape[-1]
+    targets = feat[~mask.unsqueeze(0).repeat(K, 1, 1)].reshape(K, videos.shape[0], -1, C)
+    assert per_token_rel(targets, fix["targets"]).max() < FEAT_TOL
+    out = student(videos, mask, clip_only=True)
+    assert per_token_rel(out, fix["outputs"]).max() < FEAT_TOL
+    loss = (2 - 2 * (out * targets).sum(dim=-1)).mean()
+    loss.backward()
+    g1 = {k: p.grad.clone() for k, p in student.named_parameters()}
+    for k, gr in fix["grads"].items():
+        assert cosine(g1[k], gr) >= 0.999, k
+    out2 = student(videos, mask, clip_only=True)
+    ((2 - 2 * (out2 * targets).sum(dim=-1)).mean()).backward()
+    for k, p in student.named_parameters():
+        assert rel_l2(p.grad, 2 * g1[k]) < 1e-3, f"{k}: second backward did not accumulate"
+    # eval / no-grad path and the (x_vis, x_clip) return form
+    student.eval()
+    with torch.no_grad():
+        x_vis, x_clip = student(videos, mask, clip_only=False)
+    assert per_token_rel(x_vis, fix["x_vis"]).max() < FEAT_TOL
+    assert x_clip.shape == fix["outputs"].shape
+
+
+def test_optimizer_step_matches_torch_adamw():
+    from unite_b200.engine import Stage1Engine
+    fix = load_golden("tiny_stage12.pt")
+    scfg, tcfg = oracle_cfgs(fix)
+    ssd, tsd, _ = seeded_states(fix)
+    student, teacher = _models(scfg, tcfg, ssd, tsd)
+    eng = Stage1Engine(student, teacher, mask_ratio=fix["cfg"]["mask_ratio"], lr=1e-3, weight_decay=0.05)
+    videos, q = fix["videos"].cuda(), fix["q"].cuda()
+    before = {k: v.detach().clone() for k, v in student.state_dict().items()}
+    eng.optimizer.zero_grad()
+    eng.forward_backward(videos, q)
+    grads = {k: eng.core.arena.g32(k).clone() for k in before}
+    eng.optimizer.step()
+    torch.cuda.synchronize()
+    # replay with torch.optim.AdamW on clones (decay on >=2-D weights only: optim_factory.py:83-88)
+    ps = {k: before[k].clone().requires_grad_() for k in before}
+    dec = [p for k, p in ps.items() if not (p.ndim == 1 or k.endswith(".bias"))]
+    nod = [p for k, p in ps.items() if (p.ndim == 1 or k.endswith(".bias"))]
+    opt = torch.optim.AdamW([dict(params=dec, weight_decay=0.05), dict(params=nod, weight_decay=0.0)], lr=1e-3, betas=(0.9, 0.95), eps=1e-8)
+    for k, p in ps.items():
+        p.grad = grads[k]
+    opt.step()
+    for k, p in ps.items():
+        assert rel_l2(student.state_dict()[k], p) < 1e-6, k
+    assert abs(eng.optimizer.grad_norm().item() - torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).item()) < 1e-3

@@ -22,7 +22,10 @@ def _round_up(x, a):
 
 
 class ParamArena:
-    def __init__(self, module: torch.nn.Module, device, order_key: Callable[[str], Tuple], no_decay: Callable[[str, torch.Tensor], bool]):
+    def __init__(self, module: torch.nn.Module, device, order_key: Callable[[str], Tuple], no_decay: Callable[[str, torch.Tensor], bool],
+                 gap_after: Callable[[str, torch.Tensor], int] = lambda n, p: 0):
+        """gap_after(name, p) -> number of always-zero elements reserved right after that parameter (used to make
+        [q_bias | 0 | v_bias] one contiguous 3*D vector, modeling_finetune.py:104)."""
         named = [(n, p) for n, p in module.named_parameters()]
         decay = sorted([(n, p) for n, p in named if not no_decay(n, p)], key=lambda t: order_key(t[0]))
         nodecay = sorted([(n, p) for n, p in named if no_decay(n, p)], key=lambda t: order_key(t[0]))
@@ -34,7 +37,8 @@ class ParamArena:
         self.n_decay = off
         for n, p in nodecay:
             self.offsets[n] = (off, p.numel())
-            off = _round_up(off + p.numel(), ALIGN)
+            off = _round_up(off + p.numel() + gap_after(n, p), ALIGN)
+        off = _round_up(off, 4 * ALIGN)
         self.numel = off
         self.device = torch.device(device)
         self.params = torch.zeros(off, device=device, dtype=torch.float32)

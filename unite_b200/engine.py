@@ -1,0 +1,119 @@
+"""Fused training-step engines: the bodies of the reference's train_one_epoch loops without autograd or host syncs.
+
+Stage1Engine.step == run_stage1.py:360-456 for mask_type='attention', clip_loss_type='l2', clip_loss_data='mixed',
+src_classifier=None:
+    teacher forward (no grad)                       run_stage1.py:360-377
+    attention-guided mask from Exp(1) noise         :379-387      (ub_mask_select, bit-exact given attn and q)
+    gather + project teacher targets                :389-397      (only the visible rows are ever projected)
+    student forward on visible tokens, l2 loss      :410-438
+    backward                                        :451-455  (utils.py:608-609)
+    [gradient all-reduce, unite_b200/ddp.py]        run_stage1.py:809 (DDP)
+    grad-norm + AdamW                               utils.py:610-622, optim_factory.py:162-163
+Nothing in the step reads a device value on the host: the loss and grad-norm stay on the GPU until the caller asks.
+"""
+import math
+from typing import Optional
+
+import torch
+
+from . import ops
+from .modeling_adaptation import AdaptationVisionTransformer
+from .modeling_finetune import drop_path_factors
+from .clip import VisionTransformer as ClipVisionTransformer
+
+BF16, F32, I32, U8 = torch.bfloat16, torch.float32, torch.int32, torch.uint8
+
+
+class FusedAdamW:
+    """AdamW over a ParamArena (two groups: decay / no-decay), one kernel per step; also refreshes the bf16
+    weight shadow and measures the global gradient norm (utils.py:631-643) without per-tensor kernels."""
+
+    def __init__(self, arena, lr=1.5e-4, weight_decay=0.05, betas=(0.9, 0.95), eps=1e-8):
+        self.arena = arena
+        self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.exp_avg = torch.zeros_like(arena.params)
+        self.exp_avg_sq = torch.zeros_like(arena.params)
+        self.step_count = 0
+        self.gnorm_sq = torch.zeros(1, device=arena.device, dtype=F32)
+        # the reference writes lr / weight_decay into these every step (run_stage1.py:326-338)
+        self.param_groups = [dict(name="decay", lr=lr, weight_decay=weight_decay, lr_scale=1.0),
+                             dict(name="no_decay", lr=lr, weight_decay=0.0, lr_scale=1.0)]
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.arena.grads.zero_()
+
+    def step(self, grad_scale: float = 1.0):
+        a = self.arena
+        self.step_count += 1
+        self.gnorm_sq.zero_()
+        ops.sumsq(a.grads, self.gnorm_sq)
+        g0 = self.param_groups[0]
+        ops.adamw(a.params, a.grads, self.exp_avg, self.exp_avg_sq, a.w16, a.n_decay, g0["lr"], g0["weight_decay"], self.betas[0],
+                  self.betas[1], self.eps, self.step_count, grad_scale)
+
+    def grad_norm(self, grad_scale: float = 1.0) -> torch.Tensor:
+        return self.gnorm_sq.sqrt() * grad_scale
+
+    def state_dict(self):
+        return dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, param_groups=self.param_groups)
+
+    def load_state_dict(self, sd):
+        self.step_count = sd["step"]
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.param_groups = sd["param_groups"]
+
+
+class Stage1Engine:
+    def __init__(self, student: AdaptationVisionTransformer, teacher: ClipVisionTransformer, mask_ratio: float = 0.8,
+                 lr: float = 1.5e-4, weight_decay: float = 0.05, betas=(0.9, 0.95), eps: float = 1e-8, grad_sync=None):
+        self.student, self.teacher, self.mask_ratio = student, teacher, mask_ratio
+        self.core = student.core()
+        self.core.sync_shadow(force=True)
+        self.optimizer = FusedAdamW(self.core.arena, lr, weight_decay, betas, eps)
+        self.grad_sync = grad_sync            # unite_b200.ddp.GradSync or None
+        self.share_patches = student.encoder.patch_embed.tubelet_size == teacher.kernel_size
+        self.loss = torch.zeros(1, device=self.core.arena.device, dtype=F32)
+        self.last = {}
+
+    def n_visible(self, P):
+        return P - int(P * self.mask_ratio)                      # run_stage1.py:380
+
+    def forward_backward(self, videos: torch.Tensor, q: torch.Tensor, dp: Optional[torch.Tensor] = None,
+                         attn_override: Optional[torch.Tensor] = None):
+        """Everything up to (not including) the optimizer.  videos fp32 [B,3,T,H,W] on the device; q fp32 [B*T',HW]
+        Exp(1) noise for the mask sampler.  Returns the device loss tensor [1]."""
+        core, teacher = self.core, self.teacher
+        B = videos.shape[0]
+        patches = None
+        if self.share_patches:
+            ks = teacher.kernel_size
+            n_tok = B * (videos.shape[2] // ks) * (videos.shape[3] // 16) * (videos.shape[4] // 16)
+            patches = torch.empty(n_tok, 3 * ks * 256, device=videos.device, dtype=BF16)
+            ops.patchify(videos, patches, ks)
+        layers, attn, _ = teacher.forward_features(videos, patches)
+        frames, P = attn.shape
+        Tp = frames // B
+        n_vis = self.n_visible(P)
+        mask = torch.empty(1, frames * P, device=videos.device, dtype=U8)
+        vis_idx = torch.empty(1, B, Tp * n_vis, device=videos.device, dtype=I32)
+        tea_rows = torch.empty(1, B, Tp * n_vis, device=videos.device, dtype=I32)
+        ops.mask_select(attn if attn_override is None else attn_override, q, mask, vis_idx, tea_rows, Tp, 1, n_vis)
+        targets = teacher.project_rows(layers, tea_rows.view(-1))                 # [K, B*Nv, C]
+        if dp is None and self.student.training:
+            dp = drop_path_factors(self.student.encoder.drop_path_rates, B, videos.device)
+        self.loss.zero_()
+        _, x_clip, state = core.run_forward(videos, vis_idx[0], patches if self.share_patches else None, dp, True, True,
+                                            targets=targets, loss_acc=self.loss)
+        core.run_backward(state, targets=targets)
+        self.last = dict(attn=attn, mask=mask.view(B, Tp * P).bool(), vis_idx=vis_idx[0], targets=targets, outputs=x_clip)
+        return self.loss
+
+    def step(self, videos, q, dp=None):
+        self.optimizer.zero_grad()
+        loss = self.forward_backward(videos, q, dp)
+        scale = 1.0
+        if self.grad_sync is not None:
+            scale = self.grad_sync.all_reduce(self.core.arena.grads)
+        self.optimizer.step(grad_scale=scale)
+        return loss

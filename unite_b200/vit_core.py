@@ -1,0 +1,198 @@
+"""Explicit forward / backward of the student ViT trunk on the C-ABI kernels (no autograd inside).
+
+This is the compute behind modeling_finetune.Block / Attention / Mlp / PatchEmbed (reference
+src/models/modeling_finetune.py:56-175) and AdaptationVisionTransformerEncoder.forward_features
+(src/models/modeling_adaptation.py:131-169) plus their backward.  The nn.Modules in modeling_*.py only hold
+parameters (views into a ParamArena); every FLOP of the step runs through `ops` -> libunite_b200.so.
+
+Data layout in HBM (M = B * N_tokens rows, D = embed dim):
+    residual stream x[l]      fp32 [M, D]      one buffer per layer boundary (kept for LayerNorm backward)
+    LN outputs h1/h2, attn o  bf16 [M, D]      GEMM A operands (and wgrad B operands)
+    qkv                       bf16 [M, 3D]     per row q|k|v, heads x 64
+    MLP pre-activation / act  bf16 [M, 4D]
+    lse                       fp32 [B, H, N]
+Weights are read from the arena's bf16 shadow; gradients are red.add-ed into the arena's fp32 grad buffer.
+"""
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .arena import ParamArena
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _splits_for(out_rows: int, out_cols: int, sms: int) -> int:
+    tiles = ((out_rows + 127) // 128) * ((out_cols + 255) // 256)
+    return max(1, min(32, sms // max(1, tiles)))
+
+
+class _LayerBufs:
+    __slots__ = ("h1", "qkv", "o", "lse", "x_mid", "h2", "pre", "act")
+
+
+class TrunkWorkspace:
+    """Activation storage for one (B, N) shape.  `save=True` keeps every layer's activations for backward;
+    `save=False` reuses one layer's buffers for all layers (inference)."""
+
+    def __init__(self, dev, M, B, N, D, H, hidden, depth, save):
+        self.M, self.B, self.N, self.save = M, B, N, save
+        self.busy = False
+        n_x = depth + 1 if save else 2
+        self.x = [torch.empty(M, D, device=dev, dtype=F32) for _ in range(n_x)]
+        self.layers: List[_LayerBufs] = []
+        for _ in range(depth if save else 1):
+            L = _LayerBufs()
+            L.h1 = torch.empty(M, D, device=dev, dtype=BF16)
+            L.qkv = torch.empty(M, 3 * D, device=dev, dtype=BF16)
+            L.o = torch.empty(M, D, device=dev, dtype=BF16)
+            L.lse = torch.empty(B, H, N, device=dev, dtype=F32)
+            L.x_mid = torch.empty(M, D, device=dev, dtype=F32)
+            L.h2 = torch.empty(M, D, device=dev, dtype=BF16)
+            L.pre = torch.empty(M, hidden, device=dev, dtype=BF16)
+            L.act = torch.empty(M, hidden, device=dev, dtype=BF16)
+            self.layers.append(L)
+        if save:  # backward temporaries, shared by all layers
+            self.dx = torch.empty(M, D, device=dev, dtype=F32)
+            self.dxs = torch.empty(M, D, device=dev, dtype=BF16)
+            self.d_pre = torch.empty(M, hidden, device=dev, dtype=BF16)
+            self.d_h = torch.empty(M, D, device=dev, dtype=BF16)
+            self.d_o = torch.empty(M, D, device=dev, dtype=BF16)
+            self.dqkv = torch.empty(M, 3 * D, device=dev, dtype=BF16)
+            self.d_ws = torch.empty(B, H, N, device=dev, dtype=F32)
+
+    def layer(self, l):
+        return self.layers[l if self.save else 0]
+
+    def x_at(self, l):
+        return self.x[l if self.save else l & 1]
+
+
+class ViTTrunk:
+    """patch-embed GEMM + `depth` pre-LN transformer blocks, forward and backward."""
+
+    def __init__(self, arena: ParamArena, prefix: str, D: int, depth: int, heads: int, hidden: int, eps: float):
+        assert D % heads == 0 and D // heads == 64, "the attention kernels are specialised for head_dim 64"
+        self.arena, self.prefix = arena, prefix
+        self.D, self.depth, self.H, self.hidden, self.eps = D, depth, heads, hidden, eps
+        self.scale = 64 ** -0.5
+        self.sms = ops.lib.ub_sm_count() if torch.cuda.is_available() else 148
+        self._ws: Dict = {}
+
+    # -- parameter access ---------------------------------------------------------------------
+    def w(self, name):       # bf16 shadow (GEMM operand)
+        return self.arena.b16(self.prefix + name)
+
+    def p(self, name):       # fp32 master (biases, LN affine)
+        return self.arena.p32(self.prefix + name)
+
+    def g(self, name):       # fp32 gradient
+        return self.arena.g32(self.prefix + name)
+
+    def qkv_bias(self, l):   # [q_bias | 0 | v_bias], contiguous in the arena by construction
+        o, k = self.arena.offsets[f"{self.prefix}blocks.{l}.attn.q_bias"]
+        return self.arena.params[o:o + 3 * k]
+
+    def workspace(self, B, N, save) -> TrunkWorkspace:
+        """Workspaces holding saved activations stay `busy` until their backward ran, so a second graph-attached
+        forward of the same shape (stage 3 runs several before one backward) gets its own buffers."""
+        pool = self._ws.setdefault((B, N, save), [])
+        for ws in pool:
+            if not ws.busy:
+                break
+        else:
+            ws = TrunkWorkspace(self.arena.device, B * N, B, N, self.D, self.H, self.hidden, self.depth, save)
+            pool.append(ws)
+        ws.busy = save
+        return ws
+
+    # -- forward ------------------------------------------------------------------------------
+    def forward(self, patches: torch.Tensor, pos_rows: torch.Tensor, B: int, N: int, n_layers: int, save: bool,
+                dp: Optional[torch.Tensor] = None, after_layer=None) -> TrunkWorkspace:
+        """patches bf16 [B*N, 3*tub*256] (rows already gathered), pos_rows fp32 [B*N, D].
+        dp: optional DropPath factors fp32 [depth, 2, B] (attn branch, mlp branch).
+        after_layer(l, x_out): called right after block l (its output buffer is only guaranteed to survive
+        until the next block when save=False)."""
+        ws = self.workspace(B, N, save)
+        D = self.D
+        x = ws.x_at(0)
+        ops.gemm(patches, self.w("patch_embed.proj.weight").view(D, -1), x, bias=self.p("patch_embed.proj.bias"),
+                 residual=pos_rows)
+        for l in range(n_layers):
+            L = ws.layer(l)
+            b = f"blocks.{l}."
+            ops.layernorm_fwd(x, self.p(b + "norm1.weight"), self.p(b + "norm1.bias"), self.eps, L.h1)
+            ops.gemm(L.h1, self.w(b + "attn.qkv.weight"), L.qkv, bias=self.qkv_bias(l))
+            ops.attn_fwd(L.qkv, L.o, L.lse, B, N, self.H, self.scale)
+            ops.gemm(L.o, self.w(b + "attn.proj.weight"), L.x_mid, bias=self.p(b + "attn.proj.bias"), residual=x,
+                     row_scale=None if dp is None else dp[l, 0], rows_per_scale=N)
+            ops.layernorm_fwd(L.x_mid, self.p(b + "norm2.weight"), self.p(b + "norm2.bias"), self.eps, L.h2)
+            ops.gemm(L.h2, self.w(b + "mlp.fc1.weight"), L.act, bias=self.p(b + "mlp.fc1.bias"), act=ops.UB_ACT_GELU,
+                     aux_out=L.pre if save else None)
+            xn = ws.x_at(l + 1)
+            ops.gemm(L.act, self.w(b + "mlp.fc2.weight"), xn, bias=self.p(b + "mlp.fc2.bias"), residual=L.x_mid,
+                     row_scale=None if dp is None else dp[l, 1], rows_per_scale=N)
+            x = xn
+            if after_layer is not None:
+                after_layer(l, x)
+        ws.n_layers = n_layers
+        ws.patches = patches
+        ws.dp = dp
+        return ws
+
+    # -- backward -----------------------------------------------------------------------------
+    def _wgrad(self, dy, x_in, gw):
+        """gw[out,in] += dy[M,out]^T @ x_in[M,in]  (contraction over tokens, both operands MN-major)."""
+        ops.gemm(dy, x_in, gw, a_t=True, b_t=True, accumulate=True, split_k=_splits_for(gw.shape[0], gw.shape[1], self.sms))
+
+    def backward(self, ws: TrunkWorkspace, tap_grads: Dict[int, callable], dx_init: bool = False):
+        """Back-propagates through blocks n_layers-1 .. 0 and the patch embedding.
+
+        tap_grads[l](dx_in, dxs_out, row_scale) must add the gradient arriving at the OUTPUT of block l into the
+        residual-gradient buffer ws.dx (dx_in is None when nothing has been accumulated yet) and emit
+        ws.dxs = bf16(ws.dx * row_scale).  If dx_init is True, ws.dx already holds the gradient wrt the last
+        block's output."""
+        N, D = ws.N, self.D
+        dp = ws.dp
+        have_dx = dx_init
+        nl = ws.n_layers
+        for l in reversed(range(nl)):
+            L = ws.layer(l)
+            b = f"blocks.{l}."
+            s_mlp = None if dp is None else dp[l, 1]
+            s_att = None if dp is None else dp[l, 0]
+            if l in tap_grads:
+                tap_grads[l](ws.dx if have_dx else None, ws.dxs, s_mlp)
+                have_dx = True
+            elif l == nl - 1:
+                assert have_dx, "no gradient reaches the last block"
+                ops.cast_scale_bf16(ws.dx, ws.dxs, s_mlp, N)
+            # ---- MLP branch: x_out = x_mid + s * (gelu(h2 W1^T + b1) W2^T + b2)
+            ops.gemm(ws.dxs, self.w(b + "mlp.fc2.weight"), ws.d_pre, b_t=True, act=ops.UB_ACT_DGELU, aux_in=L.pre)
+            self._wgrad(ws.dxs, L.act, self.g(b + "mlp.fc2.weight"))
+            ops.colsum_bf16(ws.dxs, self.g(b + "mlp.fc2.bias"))
+            ops.gemm(ws.d_pre, self.w(b + "mlp.fc1.weight"), ws.d_h, b_t=True)
+            self._wgrad(ws.d_pre, L.h2, self.g(b + "mlp.fc1.weight"))
+            ops.colsum_bf16(ws.d_pre, self.g(b + "mlp.fc1.bias"))
+            ops.layernorm_bwd(ws.d_h, L.x_mid, self.p(b + "norm2.weight"), self.eps, ws.dx, ws.dx, ws.dxs, s_att, N,
+                              self.g(b + "norm2.weight"), self.g(b + "norm2.bias"))
+            # ---- attention branch: x_mid = x_in + s * (attn(h1) Wp^T + bp)
+            ops.gemm(ws.dxs, self.w(b + "attn.proj.weight"), ws.d_o, b_t=True)
+            self._wgrad(ws.dxs, L.o, self.g(b + "attn.proj.weight"))
+            ops.colsum_bf16(ws.dxs, self.g(b + "attn.proj.bias"))
+            ops.attn_bwd(L.qkv, L.o, ws.d_o, L.lse, ws.d_ws, ws.dqkv, ws.B, N, self.H, self.scale)
+            ops.gemm(ws.dqkv, self.w(b + "attn.qkv.weight"), ws.d_h, b_t=True)
+            self._wgrad(ws.dqkv, L.h1, self.g(b + "attn.qkv.weight"))
+            ops.colsum_bf16(ws.dqkv[:, :D], self.g(b + "attn.q_bias"))
+            ops.colsum_bf16(ws.dqkv[:, 2 * D:], self.g(b + "attn.v_bias"))
+            # next consumer of dxs: block l-1's MLP branch (unless a tap re-emits it) or the patch embedding
+            emit = (l - 1) not in tap_grads
+            s_next = None if (dp is None or l == 0) else dp[l - 1, 1]
+            ops.layernorm_bwd(ws.d_h, ws.x_at(l), self.p(b + "norm1.weight"), self.eps, ws.dx, ws.dx,
+                              ws.dxs if emit else None, s_next, N, self.g(b + "norm1.weight"), self.g(b + "norm1.bias"))
+        # ---- patch embedding (Conv3d as GEMM): only weight and bias gradients exist
+        gw = self.g("patch_embed.proj.weight")
+        self._wgrad(ws.dxs, ws.patches, gw.view(D, -1))
+        ops.colsum_bf16(ws.dxs, self.g("patch_embed.proj.bias"))
