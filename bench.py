@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Headline benchmark: clips/s of one full stage-1 UMT distillation step (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 32]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+A "step" = teacher forward + attention-guided mask + student forward/backward + gradient all-reduce + AdamW on one
+batch of synthetic 8x224^2 clips (ViT-B/16 student, CLIP ViT-B/16 teacher, 80 % mask, per-GPU batch 32, bf16
+operands / fp32 accumulate).  Prints ONE JSON line (rank 0).  Keys follow the driver contract; in addition:
+  roofline      tensor-bound GEMM kernel family: algorithmic FLOPs / CUDA-event time of every GEMM launch of one
+                instrumented step (events on the launching stream), against the measured sustained bf16 peak
+  cpu_baseline  the CPU oracle port of the same step on this box's host cores (bounded sample, B=2)
+  e2e           the same metric through the public train_one_epoch() API with pinned-host inputs (H2D inside)
+--impl reference times the oracle port (the reference's algorithm, fp32, torch CPU) — /root/reference itself
+cannot travel to the GPU box and its own step loop does not run anywhere.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_ALG_GFLOP_PER_CLIP = 462.2          # teacher 282.5 + student fwd 60.0 + bwd 119.7 (no padding / recompute)
+NOMINAL_BF16_TFLOPS = 2250.0
+METRIC = "clips/sec (ViT-B/16 8x224^2 stage-1 step)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16=d.get("bf16_tflops_sustained", 1341.6), bf16_burst=d.get("bf16_tflops", 1640.4), hbm=d.get("hbm_gbs", 6529.1),
+                    source="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(bf16=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def build_models(seed=0):
+    import torch
+    from unite_b200.registry import create_model
+    from unite_b200 import modeling_adaptation  # noqa: F401  (registers the factories)
+    from unite_b200.clip import clip_b16
+    torch.manual_seed(seed)
+    # kwargs exactly as run_stage1.py:275-291 passes them with configs/stage1_config.yaml
+    student = create_model("adaptation_umt_base_patch16_224", pretrained=False, drop_path_rate=0.0, drop_block_rate=None,
+                           use_learnable_pos_emb=False, use_checkpoint=False, checkpoint_num=0, clip_decoder_embed_dim=768,
+                           clip_output_dim=512, clip_norm_type="l2", num_frames=8, tubelet_size=1,
+                           clip_return_layers=[6, 7, 8, 9, 10, 11], clip_student_return_interval=1, use_cls_token=False)
+    teacher = clip_b16(pretrained=False, clip_norm_type="l2", input_resolution=224, return_attn=True,
+                       clip_return_layers=[6, 7, 8, 9, 10, 11], clip_return_interval=1)
+    return student, teacher
+
+
+def cpu_reference_run(steps, warmup, batch=2, seed=0):
+    """The oracle port of the stage-1 step (fp32, torch CPU, all host threads) on a bounded sample: B=2 clips/step."""
+    import torch
+    from oracle import unite_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    student, teacher = build_models(seed)
+    ssd = {k: v.detach() for k, v in student.state_dict().items()}
+    tsd = {k: v.detach() for k, v in teacher.state_dict().items()}
+    g = torch.Generator().manual_seed(seed)
+    videos = torch.randn(batch, 3, 8, 224, 224, generator=g)
+    q = torch.empty(batch * 8, 196).exponential_(1, generator=g)
+    scfg, tcfg = O.StudentCfg(), O.TeacherCfg()
+    for _ in range(warmup):
+        O.stage1_step(ssd, tsd, videos, q, scfg, tcfg, mask_ratio=0.8)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = O.stage1_step(ssd, tsd, videos, q, scfg, tcfg, mask_ratio=0.8)
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    return dict(value=batch / dt, unit="clips/s", cores=cores, kind="port",
+                sample=f"oracle/unite_oracle.stage1_step (teacher fwd + mask + student fwd/bwd, fp32 torch CPU), B={batch} clips/step, "
+                       f"{warmup} warm-up + {steps} timed steps; optimizer not included",
+                ms_per_step=dt * 1e3, loss=float(r["loss"]))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    cb = cpu_reference_run(steps, warm)
+    line = dict(metric=METRIC, value=cb["value"], unit="clips/s", n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=cb["ms_per_step"],
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload="stage-1 UMT distillation step, ViT-B/16 student + CLIP ViT-B/16 teacher, 8x224^2, mask 0.8, tubelet 1; "
+                                     "CPU sample B=2 clips/step", global_batch=2, l2_policy="n/a (CPU)"),
+                cpu_baseline=dict(kind=cb["kind"], cores=cb["cores"], sample=cb["sample"], value=cb["value"], unit="clips/s"),
+                e2e=dict(value=cb["value"], unit="clips/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-op breakdown of one instrumented step here (json)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from unite_b200 import ops
+    from unite_b200.ddp import GradSync, DataParallel, init_distributed_from_env
+    from unite_b200.engine import Stage1Engine
+    from unite_b200.engine_for_pretraining import train_one_epoch
+    from unite_b200.synthetic import SyntheticStage1Loader
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path in unite_b200); use --impl reference for the CPU oracle")
+    rank, local, world = init_distributed_from_env()
+    dev = torch.device("cuda", local)
+    B = args.batch
+    student, teacher = build_models(seed=0)                       # identical weights on every rank (DDP broadcast equivalent)
+    student, teacher = student.to(dev).train(), teacher.to(dev).eval()
+    model = DataParallel(student)
+    model.grad_sync = GradSync() if world > 1 else None
+    eng = Stage1Engine(student, teacher, mask_ratio=0.8, lr=1.5e-4 * B * world / 256, weight_decay=0.05, grad_sync=model.grad_sync)
+
+    # ---- device-resident inputs (value) ------------------------------------------------------------------------
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    dev_batches = [(torch.randn(B, 3, 8, 224, 224, device=dev, generator=g),
+                    torch.empty(B * 8, 196, device=dev).exponential_(1, generator=g)) for _ in range(2)]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        eng.step(*dev_batches[i % 2])
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = eng.step(*dev_batches[i % 2])
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = ops.LAUNCHES - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = t.item() / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    loss_value = loss.item()
+
+    # ---- end to end through the public API: pinned host batches, H2D inside the timed region, loss read back ------
+    loader = SyntheticStage1Loader(B, steps=args.steps, seed=0, rank=rank, n_distinct=2)
+    warm_loader = SyntheticStage1Loader(B, steps=2, seed=0, rank=rank, n_distinct=1)
+
+    class _Args:
+        log_freq = 1          # read the loss back every step: the D2H of the step's result is inside the timed region
+    train_one_epoch(model, warm_loader, None, eng.optimizer, dev, 0, None, teacher_model=teacher, mask_type="attention",
+                    mask_ratio=0.8, args=_Args)
+    sync_all()
+    e0.record()
+    stats = train_one_epoch(model, loader, None, eng.optimizer, dev, 0, None, teacher_model=teacher, mask_type="attention", mask_ratio=0.8,
+                            args=_Args)
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item() / args.steps
+    e2e_value = world * B / (e2e_ms * 1e-3)
+    h2d = B * 3 * 8 * 224 * 224 * 4 + B * 8 * 196 * 4
+    d2h = 4
+
+    # ---- one instrumented step: per-op CUDA-event durations on the launching stream (roofline of the GEMM kernel) --
+    roof, breakdown = None, None
+    if rank == 0:
+        ops.PROFILE = []
+    eng.step(*dev_batches[0])          # every rank runs it (the step contains the all-reduce); only rank 0 records
+    sync_all()
+    if rank == 0:
+        peaks = measured_peaks()
+        prof, ops.PROFILE = ops.PROFILE, None
+        by = {}
+        gemm_flops = gemm_ms = 0.0
+        n_gemm = 0
+        for name, info, a, b in prof:
+            d = a.elapsed_time(b)
+            by.setdefault(name, [0, 0.0])
+            by[name][0] += 1
+            by[name][1] += d
+            if name == "gemm":
+                M, N, K = info[0], info[1], info[2]
+                gemm_flops += 2.0 * M * N * K
+                gemm_ms += d
+                n_gemm += 1
+        total_ms = sum(v[1] for v in by.values())
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel="ub::gemm_kernel (tcgen05/TMEM/TMA bf16 GEMM family, all launches of one step)",
+                    achieved=round(achieved, 1), peak=peaks["bf16"], unit="TFLOP/s", frac=round(achieved / peaks["bf16"], 4),
+                    traffic=None, peak_source=peaks["source"], launches_per_step=n_gemm,
+                    alg_flops_per_launch=gemm_flops / n_gemm, avg_launch_us=round(gemm_ms / n_gemm * 1e3, 2),
+                    share_of_step=round(gemm_ms / total_ms, 4))
+        breakdown = {k: dict(launches=v[0], ms=round(v[1], 3)) for k, v in sorted(by.items(), key=lambda kv: -kv[1][1])}
+        if args.profile_out:
+            json.dump(dict(ms_per_step_sum_of_ops=total_ms, ops=breakdown, gemm_tflops=achieved), open(args.profile_out, "w"), indent=1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference_run(steps=2, warmup=1)
+        cpu = dict(value=round(cb["value"], 3), unit="clips/s", cores=cb["cores"], kind=cb["kind"], sample=cb["sample"])
+    per_gpu = value / world
+    line = dict(
+        metric=METRIC, value=round(value, 2), unit="clips/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=round(ms_per_step, 3), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
+        config=dict(workload="BASELINE configs[1]: stage-1 UMT masked distillation, ViT-B/16 student (80% CLIP-attn mask, 320 of 1568 tokens) + "
+                             "frozen CLIP ViT-B/16 teacher, 8x224^2, tubelet 1, K=6 aligned layers, AdamW",
+                    per_gpu_batch=B, global_batch=B * world, parallelism=f"dp{world}", l2_policy="inputs_exceed_l2 (154 MB clip batch + "
+                    "multi-GB activations per step vs 126 MB L2; two input batches alternate)", init="random (reference initialisers), seed 0"),
+        clocks=clocks,
+        e2e=dict(value=round(e2e_value, 2), unit="clips/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=round(e2e_ms, 3),
+                 api="unite_b200.engine_for_pretraining.train_one_epoch (reference run_stage1.py:294 signature), pinned host batches"),
+        gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
+        mfu=dict(alg_gflop_per_clip=F_ALG_GFLOP_PER_CLIP, tflops_per_gpu=round(per_gpu * F_ALG_GFLOP_PER_CLIP / 1e3, 1),
+                 of_nominal_2250=round(per_gpu * F_ALG_GFLOP_PER_CLIP / 1e3 / NOMINAL_BF16_TFLOPS, 4),
+                 of_measured_sustained=round(per_gpu * F_ALG_GFLOP_PER_CLIP / 1e3 / measured_peaks()["bf16"], 4)),
+        loss=round(loss_value, 5), e2e_loss=round(stats["loss"], 5), op_breakdown_ms=breakdown)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

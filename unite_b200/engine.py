@@ -105,7 +105,7 @@ class Stage1Engine:
         self.loss.zero_()
         _, x_clip, state = core.run_forward(videos, vis_idx[0], patches if self.share_patches else None, dp, True, True,
                                             targets=targets, loss_acc=self.loss)
-        core.run_backward(state, targets=targets)
+        core.run_backward(state, targets=targets, grad_sync=self.grad_sync)
         self.last = dict(attn=attn, mask=mask.view(B, Tp * P).bool(), vis_idx=vis_idx[0], targets=targets, outputs=x_clip)
         return self.loss
 

@@ -1,0 +1,99 @@
+"""`train_one_epoch` for stage 1 with the reference's signature (run_stage1.py:294-303, twin
+src/engines/engine_for_pretraining_umt.py:32-40) on top of the fused Stage1Engine.
+
+What changes versus the reference loop body: no per-step `.item()` / `torch.cuda.synchronize()` (run_stage1.py:440-441,
+458) — the loss and grad-norm are accumulated on the device and read once per `log_freq` steps and at the end;
+non-finite loss is still fatal (run_stage1.py:447-449) but is checked at those read points.
+Batches are `(videos, mask_placeholder, labels[, noise])`; without `noise` the Exp(1) draw is made on the device.
+"""
+import math
+import sys
+from typing import Iterable, Optional
+
+import torch
+
+from .engine import Stage1Engine
+
+_ENGINES = {}
+
+
+def _engine_for(model, teacher_model, mask_ratio, optimizer):
+    student = model.module if hasattr(model, "module") else model
+    teacher = teacher_model.module if hasattr(teacher_model, "module") else teacher_model
+    key = (id(student), id(teacher))
+    if key not in _ENGINES:
+        gs = getattr(model, "grad_sync", None)
+        if gs is not None:
+            gs.arena = student.core().arena
+        _ENGINES[key] = Stage1Engine(student, teacher, mask_ratio=mask_ratio, grad_sync=gs)
+        if optimizer is not None and hasattr(optimizer, "arena"):
+            _ENGINES[key].optimizer = optimizer
+    return _ENGINES[key]
+
+
+def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_train_target: Optional[Iterable] = None,
+                    optimizer=None, device=None, epoch: int = 0, loss_scaler=None, max_norm: float = 0, log_writer=None,
+                    lr_scheduler=None, start_steps=0, lr_schedule_values=None, wd_schedule_values=None, src_classifier=None,
+                    teacher_model=None, clip_input_resolution=224, clip_loss_type="l2", clip_loss_ratio=0.5,
+                    mask_type="attention", mask_ratio=0.0, use_wandb=False, args=None):
+    if mask_type != "attention" or clip_loss_type != "l2" or src_classifier is not None:
+        raise NotImplementedError("the fused stage-1 path covers the shipped config: mask_type='attention', clip_loss_type='l2', "
+                                  "no source classifier (configs/stage1_config.yaml)")
+    if max_norm:
+        raise NotImplementedError("clip_grad is null in every shipped config")
+    model.train()
+    eng = _engine_for(model, teacher_model, mask_ratio, optimizer)
+    opt = eng.optimizer
+    dev = eng.core.arena.device
+    log_freq = getattr(args, "log_freq", 10) if args is not None else 10
+    loss_sum = torch.zeros(1, device=dev)
+    gn_sum = torch.zeros(1, device=dev)
+    n = 0
+    it_target = iter(data_loader_train_target) if data_loader_train_target is not None else None
+    last_loss = float("nan")
+    for step, batch in enumerate(data_loader):
+        it = start_steps + step
+        for group in opt.param_groups:                                         # run_stage1.py:326-338
+            if lr_schedule_values is not None:
+                group["lr"] = lr_schedule_values[min(it, len(lr_schedule_values) - 1)] * group.get("lr_scale", 1.0)
+            if wd_schedule_values is not None and group["weight_decay"] > 0:
+                group["weight_decay"] = wd_schedule_values[min(it, len(wd_schedule_values) - 1)]
+        videos, noise = batch[0], (batch[3] if len(batch) > 3 else None)
+        if it_target is not None:                                              # run_stage1.py:343-347
+            try:
+                tb = next(it_target)
+            except StopIteration:
+                it_target = iter(data_loader_train_target)
+                tb = next(it_target)
+            videos = torch.cat([videos, tb[0]], dim=0)
+            if noise is not None and len(tb) > 3:
+                noise = torch.cat([noise, tb[3]], dim=0)
+        videos = videos.to(dev, non_blocking=True)                             # run_stage1.py:349
+        if noise is None:
+            frames = videos.shape[0] * (videos.shape[2] // eng.teacher.kernel_size)
+            noise = torch.empty(frames, (videos.shape[3] // 16) * (videos.shape[4] // 16), device=dev).exponential_(1)
+        else:
+            noise = noise.to(dev, non_blocking=True)
+        loss = eng.step(videos, noise)
+        loss_sum += loss
+        gn_sum += opt.grad_norm(1.0 / (eng.grad_sync.world if eng.grad_sync is not None else 1))
+        n += 1
+        if log_freq and (step + 1) % log_freq == 0:
+            last_loss = loss.item()                                            # the only host read inside the loop
+            if not math.isfinite(last_loss):
+                print("Loss is {}, stopping training".format(last_loss))
+                sys.exit(1)
+        if lr_scheduler is not None:
+            lr_scheduler.step_update(start_steps + step)
+    stats = torch.cat([loss_sum, gn_sum]) / max(n, 1)
+    if torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        torch.distributed.all_reduce(stats)                                    # utils.py:239-241 (epoch-end meter sync)
+        stats /= torch.distributed.get_world_size()
+    loss_avg, gn_avg = stats.tolist()
+    if not math.isfinite(loss_avg):
+        print("Loss is {}, stopping training".format(loss_avg))
+        sys.exit(1)
+    lrs = [g["lr"] for g in opt.param_groups]
+    wds = [g["weight_decay"] for g in opt.param_groups if g["weight_decay"] > 0]
+    return {"loss": loss_avg, "loss_clip": loss_avg, "loss_scale": 1.0, "lr": max(lrs), "min_lr": min(lrs),
+            "weight_decay": wds[0] if wds else None, "grad_norm": gn_avg}

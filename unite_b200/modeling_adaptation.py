@@ -280,7 +280,11 @@ class AdaptationCore:
         state = dict(ws=ws, dws=dws, B=B, Nv=Nv, M=M, vis_flat=vis_flat, clip_only=clip_only) if save else None
         return x_vis, out.view(K, B, Nv, self.C), state
 
-    def run_backward(self, state, g_clip=None, g_vis=None, targets=None):
+    def block_grad_hi(self, l):
+        """End of the decay-segment prefix that is final once block l's backward has run (decoders + blocks >= l)."""
+        return self.arena.range_of([f"encoder.blocks.{l}.mlp.fc2.weight", f"encoder.blocks.{l}.attn.qkv.weight"])[1]
+
+    def run_backward(self, state, g_clip=None, g_vis=None, targets=None, grad_sync=None):
         """Gradient of (sum g_clip*x_clip + sum g_vis*x_vis), or — engine fast path — of the alignment loss
         mean(2 - 2<x_clip, targets>) when `targets` is given.  Parameter gradients are ACCUMULATED in the arena."""
         a = self.arena
@@ -325,7 +329,10 @@ class AdaptationCore:
             taps[l] = make_tap(l, grads)
         if (ws.n_layers - 1) not in taps:
             raise RuntimeError("no gradient reaches the last computed block (neither x_clip nor x_vis was used)")
-        self.trunk.backward(ws, taps)
+        on_done = None
+        if grad_sync is not None and grad_sync.world > 1:
+            on_done = lambda l: grad_sync.range_ready(a.grads, self.block_grad_hi(l))
+        self.trunk.backward(ws, taps, on_block_done=on_done)
         ws.busy = False
 
 

@@ -19,6 +19,34 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---- instrumentation: launch counter (bench.py's gpu_launches) and optional per-op CUDA-event timing ------------
+LAUNCHES = 0          # kernels launched through this module since import
+PROFILE = None        # set to a list to collect (name, info, start_event, end_event) per op on the launching stream
+
+
+def _instrument(name, n_kernels):
+    def deco(fn):
+        def wrapped(*a, **k):
+            global LAUNCHES
+            LAUNCHES += n_kernels
+            if PROFILE is None:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            info = None
+            if name == "gemm":
+                out = a[2]
+                K = a[0].shape[0] if k.get("a_t") else a[0].shape[1]
+                info = (out.shape[0], out.shape[1], K, bool(k.get("a_t")), bool(k.get("b_t")), out.dtype == F32)
+            PROFILE.append((name, info, e0, e1))
+            return r
+        wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+        return wrapped
+    return deco
+
+
 def _p(t: Optional[torch.Tensor], dtype=None, what="tensor") -> Optional[int]:
     if t is None:
         return None
@@ -38,6 +66,7 @@ def _p2d(t: torch.Tensor, dtype, what):
     return t.data_ptr(), t.stride(0)
 
 
+@_instrument("gemm", 1)
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=False, bias=None, residual=None,
          row_scale=None, rows_per_scale=0, act=UB_ACT_NONE, aux_in=None, aux_out=None, accumulate=False, split_k=1):
     """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).  a_t / b_t: the operand is stored transposed ([K,M] / [K,N])."""
@@ -78,19 +107,23 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=
     return out
 
 
+@_instrument("attn_fwd", 1)
 def attn_fwd(qkv, o, lse, n_seq, S, H, scale):
     check(lib.ub_attn_fwd(_p(qkv, BF16, "qkv"), _p(o, BF16, "o"), _p(lse, F32, "lse"), n_seq, S, H, scale, _stream()), "ub_attn_fwd")
 
 
+@_instrument("attn_bwd", 3)
 def attn_bwd(qkv, o, d_o, lse, d_ws, dqkv, n_seq, S, H, scale):
     check(lib.ub_attn_bwd(_p(qkv, BF16, "qkv"), _p(o, BF16, "o"), _p(d_o, BF16, "d_o"), _p(lse, F32, "lse"),
                           _p(d_ws, F32, "D_ws"), _p(dqkv, BF16, "dqkv"), n_seq, S, H, scale, _stream()), "ub_attn_bwd")
 
 
+@_instrument("cls_attn", 1)
 def cls_attn(qkv, out, n_seq, S, H, scale):
     check(lib.ub_cls_attn(_p(qkv, BF16, "qkv"), _p(out, F32, "attn"), n_seq, S, H, scale, _stream()), "ub_cls_attn")
 
 
+@_instrument("layernorm_fwd", 1)
 def layernorm_fwd(x, gamma, beta, eps, out, *, src_rows=None, post_add=None, post_idx=None):
     rows, D = out.shape
     check(lib.ub_layernorm_fwd(_p(x, F32, "ln x"), _p(src_rows, I32, "src_rows"), _p(gamma, F32, "gamma"), _p(beta, F32, "beta"),
@@ -99,11 +132,13 @@ def layernorm_fwd(x, gamma, beta, eps, out, *, src_rows=None, post_add=None, pos
     return out
 
 
+@_instrument("teacher_embed_ln", 1)
 def teacher_embed_ln(E, cls, pos, gamma, beta, eps, out, frames, P, D):
     check(lib.ub_teacher_embed_ln(_p(E, F32, "E"), _p(cls, F32, "cls"), _p(pos, F32, "pos"), _p(gamma, F32, "gamma"),
                                   _p(beta, F32, "beta"), eps, _p(out, F32, "out"), frames, P, D, _stream()), "ub_teacher_embed_ln")
 
 
+@_instrument("layernorm_bwd", 1)
 def layernorm_bwd(dy, x, gamma, eps, dx_in, dx_out, dxs_out, row_scale, rows_per_scale, dgamma, dbeta):
     rows, D = x.shape
     check(lib.ub_layernorm_bwd(_p(dy, BF16, "dy"), _p(x, F32, "x"), _p(gamma, F32, "gamma"), eps, _p(dx_in, F32, "dx_in"),
@@ -112,12 +147,14 @@ def layernorm_bwd(dy, x, gamma, eps, dx_in, dx_out, dxs_out, row_scale, rows_per
           "ub_layernorm_bwd")
 
 
+@_instrument("dec_tail_fwd", 1)
 def dec_tail_fwd(y, gamma, beta, eps, out, tgt=None, loss_acc=None, loss_scale=0.0):
     rows, D = y.shape
     check(lib.ub_dec_tail_fwd(_p(y, F32, "y"), _p(gamma, F32, "gamma"), _p(beta, F32, "beta"), eps, _p(out, F32, "out"),
                               _p(tgt, F32, "tgt"), _p(loss_acc, F32, "loss_acc"), loss_scale, rows, D, _stream()), "ub_dec_tail_fwd")
 
 
+@_instrument("dec_tail_bwd", 1)
 def dec_tail_bwd(y, gamma, beta, eps, go, go_scale, dy_out, dgamma, dbeta):
     rows, D = y.shape
     check(lib.ub_dec_tail_bwd(_p(y, F32, "y"), _p(gamma, F32, "gamma"), _p(beta, F32, "beta"), eps, _p(go, F32, "go"), go_scale,
@@ -125,11 +162,13 @@ def dec_tail_bwd(y, gamma, beta, eps, go, go_scale, dy_out, dgamma, dbeta):
           "ub_dec_tail_bwd")
 
 
+@_instrument("l2norm_rows", 1)
 def l2norm_rows(x):
     rows, D = x.shape
     check(lib.ub_l2norm_rows(_p(x, F32, "x"), rows, D, _stream()), "ub_l2norm_rows")
 
 
+@_instrument("patchify", 1)
 def patchify(x, out, tubelet):
     B, Cc, T, H, W = x.shape
     if Cc != 3:
@@ -138,12 +177,14 @@ def patchify(x, out, tubelet):
     return out
 
 
+@_instrument("mask_select", 1)
 def mask_select(attn, q, mask, vis_idx, tea_rows, T, k, n_vis):
     frames, P = attn.shape
     check(lib.ub_mask_select(_p(attn, F32, "attn"), _p(q, F32, "q"), _p(mask, U8, "mask"), _p(vis_idx, I32, "vis_idx"),
                              _p(tea_rows, I32, "tea_rows"), frames, P, T, k, n_vis, _stream()), "ub_mask_select")
 
 
+@_instrument("gather_rows", 1)
 def gather_rows(src, idx, out, rows_per_group=0, group_stride_rows=0):
     n_rows = idx.numel()
     row_bytes = out.shape[-1] * out.element_size()
@@ -152,26 +193,31 @@ def gather_rows(src, idx, out, rows_per_group=0, group_stride_rows=0):
     return out
 
 
+@_instrument("colsum_bf16", 1)
 def colsum_bf16(x, out):
     px, ld = _p2d(x, BF16, "colsum x")
     M, N = x.shape
     check(lib.ub_colsum_bf16(px, ld, _p(out, F32, "colsum out"), M, N, _stream()), "ub_colsum_bf16")
 
 
+@_instrument("cast_scale_bf16", 1)
 def cast_scale_bf16(x, out, row_scale=None, rows_per_scale=0):
     rows, D = x.shape
     check(lib.ub_cast_scale_bf16(_p(x, F32, "x"), _p(out, BF16, "out"), _p(row_scale, F32, "row_scale"), rows_per_scale, rows, D,
                                  _stream()), "ub_cast_scale_bf16")
 
 
+@_instrument("sumsq", 1)
 def sumsq(g, out):
     check(lib.ub_sumsq(_p(g, F32, "g"), g.numel(), _p(out, F32, "out"), _stream()), "ub_sumsq")
 
 
+@_instrument("adamw", 1)
 def adamw(p, g, m, v, w16, n_decay, lr, wd, beta1, beta2, eps, step, grad_scale=1.0):
     check(lib.ub_adamw(_p(p, F32, "p"), _p(g, F32, "g"), _p(m, F32, "m"), _p(v, F32, "v"), _p(w16, BF16, "w16"), p.numel(), n_decay,
                        lr, wd, beta1, beta2, eps, step, grad_scale, _stream()), "ub_adamw")
 
 
+@_instrument("cast_bf16", 1)
 def cast_bf16(x, out):
     check(lib.ub_cast_bf16(_p(x, F32, "x"), _p(out, BF16, "out"), x.numel(), _stream()), "ub_cast_bf16")

@@ -147,7 +147,7 @@ class ViTTrunk:
         """gw[out,in] += dy[M,out]^T @ x_in[M,in]  (contraction over tokens, both operands MN-major)."""
         ops.gemm(dy, x_in, gw, a_t=True, b_t=True, accumulate=True, split_k=_splits_for(gw.shape[0], gw.shape[1], self.sms))
 
-    def backward(self, ws: TrunkWorkspace, tap_grads: Dict[int, callable], dx_init: bool = False):
+    def backward(self, ws: TrunkWorkspace, tap_grads: Dict[int, callable], dx_init: bool = False, on_block_done=None):
         """Back-propagates through blocks n_layers-1 .. 0 and the patch embedding.
 
         tap_grads[l](dx_in, dxs_out, row_scale) must add the gradient arriving at the OUTPUT of block l into the
@@ -192,6 +192,8 @@ class ViTTrunk:
             s_next = None if (dp is None or l == 0) else dp[l - 1, 1]
             ops.layernorm_bwd(ws.d_h, ws.x_at(l), self.p(b + "norm1.weight"), self.eps, ws.dx, ws.dx,
                               ws.dxs if emit else None, s_next, N, self.g(b + "norm1.weight"), self.g(b + "norm1.bias"))
+            if on_block_done is not None:
+                on_block_done(l)     # every gradient of block l is final: its arena range can be all-reduced
         # ---- patch embedding (Conv3d as GEMM): only weight and bias gradients exist
         gw = self.g("patch_embed.proj.weight")
         self._wgrad(ws.dxs, ws.patches, gw.view(D, -1))
