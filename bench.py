@@ -239,10 +239,15 @@ def main():
         peaks = measured_peaks()
         prof, ops.PROFILE = ops.PROFILE, None
         by = {}
+        shapes = {}
         gemm_flops = gemm_ms = 0.0
         n_gemm = 0
         for name, info, a, b in prof:
             d = a.elapsed_time(b)
+            if name == "gemm":
+                sh = shapes.setdefault(str(info), [0, 0.0, 2.0 * info[0] * info[1] * info[2]])
+                sh[0] += 1
+                sh[1] += d
             by.setdefault(name, [0, 0.0])
             by[name][0] += 1
             by[name][1] += d
@@ -260,7 +265,10 @@ def main():
                     share_of_step=round(gemm_ms / total_ms, 4))
         breakdown = {k: dict(launches=v[0], ms=round(v[1], 3)) for k, v in sorted(by.items(), key=lambda kv: -kv[1][1])}
         if args.profile_out:
-            json.dump(dict(ms_per_step_sum_of_ops=total_ms, ops=breakdown, gemm_tflops=achieved), open(args.profile_out, "w"), indent=1)
+            gs = {k: dict(launches=v[0], ms=round(v[1], 3), us_each=round(v[1] / v[0] * 1e3, 1), tflops=round(v[2] * v[0] / (v[1] * 1e-3) / 1e12, 1))
+                  for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])}
+            json.dump(dict(ms_per_step_sum_of_ops=total_ms, ops=breakdown, gemm_tflops=achieved,
+                           gemm_shapes_M_N_K_aT_bT_fp32out=gs), open(args.profile_out, "w"), indent=1)
 
     if rank != 0:
         if world > 1:

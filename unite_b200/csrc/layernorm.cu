@@ -14,32 +14,39 @@ namespace ub {
 
 constexpr int LN_MAXV = 8;  // float4 per lane -> D <= 1024
 
-struct RowF {
-  float4 v[LN_MAXV];
+// One row distributed over a warp: lane holds float4 chunks i*32+lane, i < NV (NV = D/128 is a template
+// parameter so the row occupies exactly NV*4 registers and every loop is fully unrolled without predicates).
+template <int NV>
+struct RowT {
+  float4 v[NV];
 };
 
-UB_DEVINL void row_load_f32(RowF& r, const float* p, int nv, int lane) {
+template <int NV>
+UB_DEVINL void row_load_f32(RowT<NV>& r, const float* p, int nv, int lane) {
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
+  for (int i = 0; i < NV; ++i)
     if (i < nv) r.v[i] = *reinterpret_cast<const float4*>(p + (i * 32 + lane) * 4);
 }
-UB_DEVINL void row_load_bf16(RowF& r, const bf16* p, int nv, int lane) {
+template <int NV>
+UB_DEVINL void row_load_bf16(RowT<NV>& r, const bf16* p, int nv, int lane) {
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
+  for (int i = 0; i < NV; ++i)
     if (i < nv) {
       const uint2 u = *reinterpret_cast<const uint2*>(p + (i * 32 + lane) * 4);
       const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
       r.v[i] = make_float4(a.x, a.y, b.x, b.y);
     }
 }
-UB_DEVINL void row_store_f32(const RowF& r, float* p, int nv, int lane) {
+template <int NV>
+UB_DEVINL void row_store_f32(const RowT<NV>& r, float* p, int nv, int lane) {
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
+  for (int i = 0; i < NV; ++i)
     if (i < nv) *reinterpret_cast<float4*>(p + (i * 32 + lane) * 4) = r.v[i];
 }
-UB_DEVINL void row_store_bf16(const RowF& r, bf16* p, int nv, int lane) {
+template <int NV>
+UB_DEVINL void row_store_bf16(const RowT<NV>& r, bf16* p, int nv, int lane) {
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
+  for (int i = 0; i < NV; ++i)
     if (i < nv) {
       uint2 u;
       u.x = pack_bf16x2(r.v[i].x, r.v[i].y);
@@ -47,26 +54,29 @@ UB_DEVINL void row_store_bf16(const RowF& r, bf16* p, int nv, int lane) {
       *reinterpret_cast<uint2*>(p + (i * 32 + lane) * 4) = u;
     }
 }
-UB_DEVINL float row_sum(const RowF& r, int nv) {
+template <int NV>
+UB_DEVINL float row_sum(const RowT<NV>& r, int nv) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
+  for (int i = 0; i < NV; ++i)
     if (i < nv) s += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
   return warp_sum(s);
 }
-UB_DEVINL float row_dot(const RowF& a, const RowF& b, int nv) {
+template <int NV>
+UB_DEVINL float row_dot(const RowT<NV>& a, const RowT<NV>& b, int nv) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
+  for (int i = 0; i < NV; ++i)
     if (i < nv) s += a.v[i].x * b.v[i].x + a.v[i].y * b.v[i].y + a.v[i].z * b.v[i].z + a.v[i].w * b.v[i].w;
   return warp_sum(s);
 }
 // two-pass mean / rstd (matches torch's fp32 layer_norm to round-off); leaves x centred: x <- x - mean
-UB_DEVINL float row_center_rstd(RowF& x, int nv, int D, float eps) {
+template <int NV>
+UB_DEVINL float row_center_rstd(RowT<NV>& x, int nv, int D, float eps) {
   const float mean = row_sum(x, nv) / (float)D;
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
+  for (int i = 0; i < NV; ++i)
     if (i < nv) {
       x.v[i].x -= mean; x.v[i].y -= mean; x.v[i].z -= mean; x.v[i].w -= mean;
       s += x.v[i].x * x.v[i].x + x.v[i].y * x.v[i].y + x.v[i].z * x.v[i].z + x.v[i].w * x.v[i].w;
@@ -74,7 +84,7 @@ UB_DEVINL float row_center_rstd(RowF& x, int nv, int D, float eps) {
   s = warp_sum(s);
   return rsqrtf(s / (float)D + eps);
 }
-#define UB_ROW_FOREACH(i, nv) _Pragma("unroll") for (int i = 0; i < LN_MAXV; ++i) if (i < nv)
+#define UB_ROW_FOREACH(i, nv) _Pragma("unroll") for (int i = 0; i < NV; ++i) if (i < nv)
 
 // ------------------------------------------------------------------------------------------------
 // forward:  out[r] = LN(x[src(r)]) * gamma + beta  (+ post_add[post_idx[r]])
@@ -92,26 +102,27 @@ struct LnFwdArgs {
   float eps;
 };
 
+template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
   const int lane = threadIdx.x & 31;
-  const int nv = a.D >> 7;
+  constexpr int nv = NV;
   const int wpb = blockDim.x >> 5;
-  RowF g, b;
-  row_load_f32(g, a.gamma, nv, lane);
-  row_load_f32(b, a.beta, nv, lane);
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < a.rows; row += gridDim.x * wpb) {
     const int64_t src = a.src_rows ? a.src_rows[row] : row;
-    RowF x;
+    RowT<NV> x;
     row_load_f32(x, a.x + src * a.D, nv, lane);
     const float rstd = row_center_rstd(x, nv, a.D, a.eps);
-    UB_ROW_FOREACH(i, nv) {
-      x.v[i].x = x.v[i].x * rstd * g.v[i].x + b.v[i].x;
-      x.v[i].y = x.v[i].y * rstd * g.v[i].y + b.v[i].y;
-      x.v[i].z = x.v[i].z * rstd * g.v[i].z + b.v[i].z;
-      x.v[i].w = x.v[i].w * rstd * g.v[i].w + b.v[i].w;
+    UB_ROW_FOREACH(i, nv) {   // gamma / beta come from L1 every row: keeps the kernel at ~40 registers -> full occupancy
+      float4 g, b;
+      asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "l"(a.gamma + (i * 32 + lane) * 4));
+      asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(a.beta + (i * 32 + lane) * 4));
+      x.v[i].x = x.v[i].x * rstd * g.x + b.x;
+      x.v[i].y = x.v[i].y * rstd * g.y + b.y;
+      x.v[i].z = x.v[i].z * rstd * g.z + b.z;
+      x.v[i].w = x.v[i].w * rstd * g.w + b.w;
     }
     if (a.post_add) {
-      RowF pa;
+      RowT<NV> pa;
       row_load_f32(pa, a.post_add + (int64_t)a.post_idx[row] * a.D, nv, lane);
       UB_ROW_FOREACH(i, nv) {
         x.v[i].x += pa.v[i].x; x.v[i].y += pa.v[i].y; x.v[i].z += pa.v[i].z; x.v[i].w += pa.v[i].w;
@@ -125,20 +136,21 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
 // ------------------------------------------------------------------------------------------------
 // teacher token assembly + ln_pre (clip.py:150-152): row (f, tok):  tok==0 ? cls : E[f*P + tok-1], + pos[tok], LN
 // ------------------------------------------------------------------------------------------------
+template <int NV>
 __global__ void __launch_bounds__(256) teacher_embed_ln_kernel(const float* __restrict__ E, const float* __restrict__ cls,
                                                                const float* __restrict__ pos, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float* __restrict__ out,
                                                                int frames, int P, int D, float eps) {
   const int lane = threadIdx.x & 31;
-  const int nv = D >> 7;
+  constexpr int nv = NV;
   const int wpb = blockDim.x >> 5;
   const int rows = frames * (P + 1);
-  RowF g, b;
+  RowT<NV> g, b;
   row_load_f32(g, gamma, nv, lane);
   row_load_f32(b, beta, nv, lane);
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
     const int f = row / (P + 1), tok = row % (P + 1);
-    RowF x, pe;
+    RowT<NV> x, pe;
     if (tok == 0) row_load_f32(x, cls, nv, lane);
     else row_load_f32(x, E + ((int64_t)f * P + tok - 1) * D, nv, lane);
     row_load_f32(pe, pos + (int64_t)tok * D, nv, lane);
@@ -178,7 +190,8 @@ struct LnBwdArgs {
 };
 
 // block-wide reduction of per-warp column partials, then one red.add per column per block
-UB_DEVINL void block_col_reduce_atomic(const RowF& part, float* s_buf, float* gdst, int nv, int D) {
+template <int NV>
+UB_DEVINL void block_col_reduce_atomic(const RowT<NV>& part, float* s_buf, float* gdst, int nv, int D) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   __syncthreads();
   row_store_f32(part, s_buf + warp * D, nv, lane);
@@ -190,12 +203,13 @@ UB_DEVINL void block_col_reduce_atomic(const RowF& part, float* s_buf, float* gd
   }
 }
 
+template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
   extern __shared__ float s_red[];  // [warps][D]
   const int lane = threadIdx.x & 31;
-  const int nv = a.D >> 7;
+  constexpr int nv = NV;
   const int wpb = blockDim.x >> 5;
-  RowF g, dgam, dbet;
+  RowT<NV> g, dgam, dbet;
   row_load_f32(g, a.gamma, nv, lane);
   UB_ROW_FOREACH(i, nv) {
     dgam.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -203,7 +217,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
   }
   const float invD = 1.f / (float)a.D;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < a.rows; row += gridDim.x * wpb) {
-    RowF x, dy;
+    RowT<NV> x, dy;
     row_load_f32(x, a.x + (int64_t)row * a.D, nv, lane);
     row_load_bf16(dy, a.dy + (int64_t)row * a.D, nv, lane);
     const float rstd = row_center_rstd(x, nv, a.D, a.eps);
@@ -220,7 +234,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
     }
     s1 = warp_sum(s1) * invD;
     s2 = warp_sum(s2) * invD;
-    RowF dx;
+    RowT<NV> dx;
     if (a.dx_in) row_load_f32(dx, a.dx_in + (int64_t)row * a.D, nv, lane);
     UB_ROW_FOREACH(i, nv) {
       if (!a.dx_in) dx.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -244,20 +258,21 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
 // decoder tail (modeling_adaptation.py:203-213): out = u / ||u||,  u = LN(y)*gamma + beta        (fp32 in/out)
 // optionally also accumulates the alignment loss  sum_rows (2 - 2 <out, tgt>) * loss_scale  (run_stage1.py:431)
 // ------------------------------------------------------------------------------------------------
+template <int NV>
 __global__ void __launch_bounds__(256) dec_tail_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float* __restrict__ out,
                                                            const float* __restrict__ tgt, float* __restrict__ loss_acc,
                                                            float loss_scale, int rows, int D, float eps) {
   __shared__ float s_loss[8];
   const int lane = threadIdx.x & 31;
-  const int nv = D >> 7;
+  constexpr int nv = NV;
   const int wpb = blockDim.x >> 5;
-  RowF g, b;
+  RowT<NV> g, b;
   row_load_f32(g, gamma, nv, lane);
   row_load_f32(b, beta, nv, lane);
   float lacc = 0.f;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
-    RowF x;
+    RowT<NV> x;
     row_load_f32(x, y + (int64_t)row * D, nv, lane);
     const float rstd = row_center_rstd(x, nv, D, eps);
     UB_ROW_FOREACH(i, nv) {
@@ -270,7 +285,7 @@ __global__ void __launch_bounds__(256) dec_tail_fwd_kernel(const float* __restri
     UB_ROW_FOREACH(i, nv) { x.v[i].x *= inv; x.v[i].y *= inv; x.v[i].z *= inv; x.v[i].w *= inv; }
     row_store_f32(x, out + (int64_t)row * D, nv, lane);
     if (tgt) {
-      RowF t;
+      RowT<NV> t;
       row_load_f32(t, tgt + (int64_t)row * D, nv, lane);
       lacc += 2.0f - 2.0f * row_dot(x, t, nv);
     }
@@ -289,15 +304,16 @@ __global__ void __launch_bounds__(256) dec_tail_fwd_kernel(const float* __restri
 // backward of the decoder tail.  Upstream gradient wrt `out` is  go_scale * go[row]  (the engine passes
 // go = targets, go_scale = -2/rows_total for the l2 alignment loss; autograd passes grad_output, 1).
 //   du = (go - out*<out,go>) / ||u|| ;  dy = LNbwd(du)  -> bf16 ;  dgamma/dbeta accumulated.
+template <int NV>
 __global__ void __launch_bounds__(256) dec_tail_bwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, const float* __restrict__ go,
                                                            float go_scale, bf16* __restrict__ dy_out, float* __restrict__ dgamma,
                                                            float* __restrict__ dbeta, int rows, int D, float eps) {
   extern __shared__ float s_red[];
   const int lane = threadIdx.x & 31;
-  const int nv = D >> 7;
+  constexpr int nv = NV;
   const int wpb = blockDim.x >> 5;
-  RowF g, b, dgam, dbet;
+  RowT<NV> g, b, dgam, dbet;
   row_load_f32(g, gamma, nv, lane);
   row_load_f32(b, beta, nv, lane);
   UB_ROW_FOREACH(i, nv) {
@@ -306,7 +322,7 @@ __global__ void __launch_bounds__(256) dec_tail_bwd_kernel(const float* __restri
   }
   const float invD = 1.f / (float)D;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
-    RowF x, u, du;
+    RowT<NV> x, u, du;
     row_load_f32(x, y + (int64_t)row * D, nv, lane);
     row_load_f32(du, go + (int64_t)row * D, nv, lane);
     const float rstd = row_center_rstd(x, nv, D, eps);
@@ -343,18 +359,29 @@ __global__ void __launch_bounds__(256) dec_tail_bwd_kernel(const float* __restri
 }
 
 // x[row] /= ||x[row]||   (teacher targets, clip.py:173)
+template <int NV>
 __global__ void __launch_bounds__(256) l2norm_rows_kernel(float* __restrict__ x, int rows, int D) {
   const int lane = threadIdx.x & 31;
-  const int nv = D >> 7;
+  constexpr int nv = NV;
   const int wpb = blockDim.x >> 5;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
-    RowF v;
+    RowT<NV> v;
     row_load_f32(v, x + (int64_t)row * D, nv, lane);
     const float inv = 1.0f / sqrtf(row_dot(v, v, nv));
     UB_ROW_FOREACH(i, nv) { v.v[i].x *= inv; v.v[i].y *= inv; v.v[i].z *= inv; v.v[i].w *= inv; }
     row_store_f32(v, x + (int64_t)row * D, nv, lane);
   }
 }
+
+#define UB_LN_DISPATCH(D, KERNEL, GRID, SMEM, STREAM, ...)                                   \
+  switch ((D) >> 7) {                                                                         \
+    case 1: KERNEL<1><<<GRID, 256, SMEM, STREAM>>>(__VA_ARGS__); break;                       \
+    case 2: KERNEL<2><<<GRID, 256, SMEM, STREAM>>>(__VA_ARGS__); break;                       \
+    case 4: KERNEL<4><<<GRID, 256, SMEM, STREAM>>>(__VA_ARGS__); break;                       \
+    case 6: KERNEL<6><<<GRID, 256, SMEM, STREAM>>>(__VA_ARGS__); break;                       \
+    case 8: KERNEL<8><<<GRID, 256, SMEM, STREAM>>>(__VA_ARGS__); break;                       \
+    default: break;                                                                           \
+  }
 
 static int ln_grid(int rows) {
   const int want = (rows + 7) / 8;
@@ -367,7 +394,7 @@ static int ln_bwd_grid(int rows) {
   return want < cap ? want : cap;
 }
 static int check_D(int D, const char* who) {
-  UB_REQUIRE(D % 128 == 0 && D >= 128 && D <= 128 * LN_MAXV, "%s: feature dim must be a multiple of 128 in [128,1024] (D=%d)", who, D);
+  UB_REQUIRE(D == 128 || D == 256 || D == 512 || D == 768 || D == 1024, "%s: feature dim must be one of 128/256/512/768/1024 (D=%d)", who, D);
   return 0;
 }
 
@@ -383,7 +410,7 @@ extern "C" int ub_layernorm_fwd(const float* x, const int* src_rows, const float
   UB_REQUIRE((post_add == nullptr) == (post_idx == nullptr), "layernorm_fwd: post_add and post_idx go together");
   if (check_D(D, "layernorm_fwd")) return 1;
   LnFwdArgs a{x, src_rows, gamma, beta, post_add, post_idx, out, out_fp32, rows, D, eps};
-  ln_fwd_kernel<<<ln_grid(rows), 256, 0, (cudaStream_t)stream>>>(a);
+  UB_LN_DISPATCH(D, ln_fwd_kernel, ln_grid(rows), 0, (cudaStream_t)stream, a)
   return check_launch("ln_fwd_kernel");
 }
 
@@ -391,8 +418,7 @@ extern "C" int ub_teacher_embed_ln(const float* E, const float* cls, const float
                                    const float* beta, float eps, float* out, int frames, int P, int D, void* stream) {
   UB_REQUIRE(E && cls && pos && gamma && beta && out, "teacher_embed_ln: null pointer");
   if (check_D(D, "teacher_embed_ln")) return 1;
-  teacher_embed_ln_kernel<<<ln_grid(frames * (P + 1)), 256, 0, (cudaStream_t)stream>>>(E, cls, pos, gamma, beta, out, frames, P,
-                                                                                        D, eps);
+  UB_LN_DISPATCH(D, teacher_embed_ln_kernel, ln_grid(frames * (P + 1)), 0, (cudaStream_t)stream, E, cls, pos, gamma, beta, out, frames, P, D, eps)
   return check_launch("teacher_embed_ln_kernel");
 }
 
@@ -403,7 +429,7 @@ extern "C" int ub_layernorm_bwd(const void* dy, const float* x, const float* gam
   UB_REQUIRE(row_scale == nullptr || rows_per_scale > 0, "layernorm_bwd: rows_per_scale must be > 0");
   if (check_D(D, "layernorm_bwd")) return 1;
   LnBwdArgs a{(const bf16*)dy, x, gamma, dx_in, dx_out, (bf16*)dxs_out, row_scale, rows_per_scale, dgamma, dbeta, rows, D, eps};
-  ln_bwd_kernel<<<ln_bwd_grid(rows), 256, 8 * D * sizeof(float), (cudaStream_t)stream>>>(a);
+  UB_LN_DISPATCH(D, ln_bwd_kernel, ln_bwd_grid(rows), 8 * D * sizeof(float), (cudaStream_t)stream, a)
   return check_launch("ln_bwd_kernel");
 }
 
@@ -412,8 +438,7 @@ extern "C" int ub_dec_tail_fwd(const float* y, const float* gamma, const float* 
   UB_REQUIRE(y && gamma && beta && out, "dec_tail_fwd: null pointer");
   UB_REQUIRE((tgt == nullptr) || (loss_acc != nullptr), "dec_tail_fwd: tgt needs loss_acc");
   if (check_D(D, "dec_tail_fwd")) return 1;
-  dec_tail_fwd_kernel<<<ln_grid(rows), 256, 0, (cudaStream_t)stream>>>(y, gamma, beta, out, tgt, loss_acc, loss_scale, rows, D,
-                                                                      eps);
+  UB_LN_DISPATCH(D, dec_tail_fwd_kernel, ln_grid(rows), 0, (cudaStream_t)stream, y, gamma, beta, out, tgt, loss_acc, loss_scale, rows, D, eps)
   return check_launch("dec_tail_fwd_kernel");
 }
 
@@ -421,14 +446,14 @@ extern "C" int ub_dec_tail_bwd(const float* y, const float* gamma, const float* 
                                float go_scale, void* dy_out, float* dgamma, float* dbeta, int rows, int D, void* stream) {
   UB_REQUIRE(y && gamma && beta && go && dy_out && dgamma && dbeta, "dec_tail_bwd: null pointer");
   if (check_D(D, "dec_tail_bwd")) return 1;
-  dec_tail_bwd_kernel<<<ln_bwd_grid(rows), 256, 8 * D * sizeof(float), (cudaStream_t)stream>>>(
-      y, gamma, beta, go, go_scale, (bf16*)dy_out, dgamma, dbeta, rows, D, eps);
+  UB_LN_DISPATCH(D, dec_tail_bwd_kernel, ln_bwd_grid(rows), 8 * D * sizeof(float), (cudaStream_t)stream, y, gamma, beta, go, go_scale,
+                 (bf16*)dy_out, dgamma, dbeta, rows, D, eps)
   return check_launch("dec_tail_bwd_kernel");
 }
 
 extern "C" int ub_l2norm_rows(float* x, int rows, int D, void* stream) {
   UB_REQUIRE(x != nullptr && rows > 0, "l2norm_rows: bad arguments");
   if (check_D(D, "l2norm_rows")) return 1;
-  l2norm_rows_kernel<<<ln_grid(rows), 256, 0, (cudaStream_t)stream>>>(x, rows, D);
+  UB_LN_DISPATCH(D, l2norm_rows_kernel, ln_grid(rows), 0, (cudaStream_t)stream, x, rows, D)
   return check_launch("l2norm_rows_kernel");
 }

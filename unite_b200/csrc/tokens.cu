@@ -116,24 +116,48 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint4* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// column sums of a bf16 matrix (bias gradients), accumulated into fp32 with red.add
-// block = 128 threads x 2 columns, 256 rows per block
+// column sums of a bf16 matrix (bias gradients), accumulated into fp32 with red.add.
+// CTA = 256 threads = 8 row-groups x 32 lanes; a lane owns 8 columns (one 16-byte load per row), the CTA covers
+// 256 columns x ROWS_PER_CTA rows with 4 independent loads in flight per thread, then reduces the 8 row-groups
+// through smem and issues one red.add per column.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) colsum_bf16_kernel(const bf16* __restrict__ x, int64_t ld, float* __restrict__ out,
+constexpr int CS_ROWS = 128;
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ x, int64_t ld, float* __restrict__ out,
                                                           int M, int N) {
-  const int col = (blockIdx.x * 128 + threadIdx.x) * 2;
-  if (col >= N) return;
-  const int r0 = blockIdx.y * 256;
-  const int r1 = min(M, r0 + 256);
-  float a0 = 0.f, a1 = 0.f;
-#pragma unroll 8
-  for (int r = r0; r < r1; ++r) {
-    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + (int64_t)r * ld + col));
-    a0 += v.x;
-    a1 += v.y;
+  __shared__ float s_part[8][256];
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  const int r0 = blockIdx.y * CS_ROWS;
+  const int r1 = min(M, r0 + CS_ROWS);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (col < N) {
+    for (int r = r0 + rg; r < r1; r += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = (r + u * 8 < r1) ? ldg_nc_v4(x + (int64_t)(r + u * 8) * ld + col) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float2 f;
+        f = unpack_bf16x2(v[u].x); acc[0] += f.x; acc[1] += f.y;
+        f = unpack_bf16x2(v[u].y); acc[2] += f.x; acc[3] += f.y;
+        f = unpack_bf16x2(v[u].z); acc[4] += f.x; acc[5] += f.y;
+        f = unpack_bf16x2(v[u].w); acc[6] += f.x; acc[7] += f.y;
+      }
+    }
   }
-  atomicAdd(out + col, a0);
-  atomicAdd(out + col + 1, a1);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_part[rg][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s += s_part[g][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
 }
 
 // out_bf16 = bf16(x * row_scale[row / rows_per_scale])   (fp32 -> bf16 cast of the residual-stream gradient)
@@ -198,9 +222,10 @@ extern "C" int ub_gather_rows(const void* in, const int* idx, void* out, int64_t
 }
 
 extern "C" int ub_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, void* stream) {
-  UB_REQUIRE(x && out && M > 0 && N > 0 && N % 2 == 0, "colsum_bf16: bad arguments M=%d N=%d", M, N);
-  dim3 grid((N / 2 + 127) / 128, (M + 255) / 256);
-  colsum_bf16_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, M, N);
+  UB_REQUIRE(x && out && M > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "colsum_bf16: N and ld must be multiples of 8 (M=%d N=%d)", M, N);
+  UB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "colsum_bf16: x must be 16-byte aligned");
+  dim3 grid((N + 255) / 256, (M + CS_ROWS - 1) / CS_ROWS);
+  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, M, N);
   return check_launch("colsum_bf16_kernel");
 }
 
