@@ -3,18 +3,25 @@
 // Replaces every dense contraction of the UNITE step (see include/unite_b200.h for the reference
 // call sites).  Design (B200-first, nothing like the reference's cuBLAS calls):
 //   * persistent CTAs (one per SM), static round-robin over (m-tile, n-tile, k-split) work items;
+//     wide tiles run as CTA PAIRS (cluster of 2, tcgen05 cta_group::2): 256 x 256 per pair, each CTA keeps its own
+//     128 rows of A and half of B in smem;
 //   * warp 0  : TMA producer  (cp.async.bulk.tensor, 128B-swizzled boxes, STAGES-deep mbarrier ring);
-//   * warp 1  : single-thread tcgen05.mma issuer, 128 x BN x 16 UMMA, accumulators in TMEM,
-//               two accumulator stages (2*BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
-//   * warps 2-9: epilogue, tcgen05.ld 32x32b -> registers -> swizzled smem transpose -> fused bias / activation /
-//               DropPath scale / residual with fully coalesced 128-bit global loads and stores
-//               (or red.global.add.v4.f32 for split-K weight gradients).
+//   * warp 1  : single-thread tcgen05.mma issuer (leader CTA of a pair), accumulators in TMEM, two accumulator
+//               stages (2*BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * warps 2-9: epilogue.  tcgen05.ld gives each lane one accumulator ROW; bias / activation / DropPath scale are
+//               applied in registers, the 32-row slab is written to a 128B-swizzled smem staging buffer and leaves
+//               through the TMA engine (bulk tensor store, or cp.reduce.async.bulk .add for split-K weight
+//               gradients).  The fp32 residual and the bf16 GELU pre-activation ARRIVE through TMA too (loaded
+//               one slab ahead into the same staging buffers and combined in place), so the epilogue issues no
+//               per-thread global loads/stores, no address arithmetic and no bounds checks (TMA clips).
 //   * operands may be K-major (activations, weights [out,in]) or MN-major (the same row-major tensors
 //     contracted over their ROW index: dgrad uses W as B^T, wgrad contracts over tokens) — no transposes
 //     are ever materialised.
 #include "common.cuh"
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include "../../include/unite_b200.h"
 
 namespace ub {
@@ -22,45 +29,58 @@ namespace ub {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_BYTES = 8 * 2 * 4096;   // 8 epilogue warps x 2 staging slabs of 32 rows x 128 B
 
 struct GemmParams {
-  void* C;
-  int64_t ldc;
   int M, N, K;
   int splits, kb_per_split;
-  ub_gemm_epilogue ep;
+  const float* bias;
+  const float* row_scale;
+  int rows_per_scale;
+  int act;
+  int accumulate;
+  int has_aux_out;
 };
 
-// EPI: 0 = bias/activation only, 1 = + fp32 residual, 2 = DGELU (reads the bf16 pre-activation)
-// NCTA: 1 = one CTA per 128 x BN tile; 2 = a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256 x BN tile: each CTA
-//       holds its own 128 rows of A and HALF of B, which cuts the smem fill + operand-read traffic per MMA by a third.
-template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, int NCTA>
+// EPI : 0 = bias / activation (/ pre-activation copy), 1 = + fp32 residual (fp32 out), 2 = DGELU: * gelu'(aux) (bf16 out)
+// OUT32: C is fp32 (32-column slabs) or bf16 (64-column slabs); both give 128-byte staging rows
+// NCTA: 1 = one CTA per 128 x BN tile; 2 = CTA pair per 256 x BN tile
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, bool OUT32, int NCTA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+            const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
   constexpr int BN_L = BN / NCTA;            // rows of B resident in this CTA
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN_L * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // 256 or 512: power of two
   constexpr uint32_t IDESC = umma_idesc_bf16(BM * NCTA, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  constexpr int CW = OUT32 ? 32 : 64;        // columns per epilogue slab
+  constexpr int SLABS = (BN / 2) / CW;       // slabs per warp per tile
+  static_assert(EPI != 1 || OUT32, "residual epilogue writes fp32");
+  static_assert(EPI != 2 || !OUT32, "DGELU epilogue writes bf16");
   const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* epi_s = smem + STAGES * STAGE_BYTES;                       // [8 warps][2][4096], 1024-aligned
+  float* bias_s = reinterpret_cast<float*>(epi_s + EPI_BYTES);         // [2][BN]
+  uint64_t* full = reinterpret_cast<uint64_t*>(bias_s + 2 * BN);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  uint8_t* epi_s = smem + STAGES * STAGE_BYTES + 256;  // 8 warps x 4 KB epilogue staging (after the barriers)
+  uint64_t* rbar = tempty + 2;                                         // [8 warps][2] residual / aux slab arrived
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();   // swizzled TMA / UMMA tiles need the 1024-byte alignment
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -69,6 +89,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 8 * NCTA);   // the leader's copy collects the epilogue warps of both CTAs
     }
+    for (int i = 0; i < 16; ++i) mbar_init(&rbar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -192,125 +213,157 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 2) {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
-    // Two warps per TMEM sub-partition, each owning half of the tile's columns, 32 columns at a time:
-    //   phase 1  tcgen05.ld gives every lane one ROW (32 fp32) -> written to this warp's private 4 KB smem
-    //            staging tile with a 16-byte XOR swizzle (conflict-free);
-    //   phase 2  the tile is read back so that 8 consecutive lanes hold one row's 128 contiguous bytes, and ALL
-    //            global traffic of the epilogue (bias, residual, aux, output, red.add) is issued in that layout:
-    //            a warp instruction touches 4 full 128 B lines instead of 32 partial ones.
-    // Global operands are prefetched one chunk ahead so their latency hides behind TMEM/smem work.
+    const int we = warp - 2;
     const int sp = warp & 3;            // TMEM sub-partition this warp may read
-    const int half = (warp - 2) >> 2;   // which half of the BN columns
-    constexpr int CHUNKS = BN / 64;     // 32-column chunks per warp
-    uint8_t* stg = epi_s + (warp - 2) * 4096;
-    const uint32_t stg_a = smem_u32(stg);
-    const int sub_r = lane >> 3;        // phase-2: row within a group of 4
-    const int c4 = lane & 7;            // phase-2: 16-byte chunk (4 fp32 columns) of the 32-column slab
+    const int half = we >> 2;           // which half of the BN columns
+    const int etid = threadIdx.x - 64;  // 0..255
+    uint8_t* const slab0 = epi_s + we * 8192;          // two 4 KB staging slabs: slab0 + (b << 12)
+    const uint32_t slab0_a = smem_u32(slab0);
+    uint64_t* rb = rbar + we * 2;
+    const uint32_t sw = (uint32_t)(lane & 7);      // 16-byte chunk XOR of this lane's row (128B swizzle)
+    const uint32_t rowoff = (uint32_t)lane * 128u;
     int as = 0;
     uint32_t aphase = 0;
-    const ub_gemm_epilogue& ep = p.ep;
-    constexpr bool has_res = EPI == 1;
-    constexpr bool has_aux_in = EPI == 2;
+    uint32_t cc = 0;                    // running slab counter of this warp: staging buffer = cc & 1
+    // (row, col) of this warp's slab `c` of work item `w`
+    auto slab_row = [&](int w) { return ((w / p.splits) / n_tiles) * (BM * NCTA) + (int)cta_rank * BM + sp * 32; };
+    auto slab_col = [&](int w, int c) { return ((w / p.splits) % n_tiles) * BN + half * (BN / 2) + c * CW; };
+    if (EPI != 0 && w_first < total_work && lane == 0) {
+      // residual / pre-activation slab of the very first (tile, slab) of this warp
+      mbar_expect_tx(&rb[0], 4096);
+      tma_load_2d(&tmR, &rb[0], slab0, slab_col(w_first, 0), slab_row(w_first));
+    }
     for (int w = w_first; w < total_work; w += w_step) {
-      const int tile = w / p.splits;
-      const int m0 = (tile / n_tiles) * (BM * NCTA) + (int)cta_rank * BM;
-      const int n0 = (tile % n_tiles) * BN;
-      const int row_base = m0 + sp * 32;
-      const int cbase = n0 + half * (BN / 2);
-      // per-tile operands in the phase-2 layout
-      float rs[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int row = row_base + it * 4 + sub_r;
-        rs[it] = (ep.row_scale != nullptr && row < p.M) ? __ldg(ep.row_scale + row / ep.rows_per_scale) : 1.0f;
+      const int n0 = ((w / p.splits) % n_tiles) * BN;
+      const int row0 = slab_row(w);
+      float* bias_tile = bias_s + as * BN;
+      if (p.bias != nullptr) {
+        if (etid < BN) bias_tile[etid] = (n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.0f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      float4 rn[has_res ? 8 : 1];
-      uint2 an[has_aux_in ? 8 : 1];
-      float4 bn;
-      auto prefetch = [&](int c) {
-        const int col = cbase + c * 32 + c4 * 4;
-        bn = (ep.bias != nullptr && col < p.N) ? __ldg(reinterpret_cast<const float4*>(ep.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = row_base + it * 4 + sub_r;
-          const bool ok = row < p.M && col < p.N;
-          if constexpr (has_res)
-            rn[it] = ok ? *reinterpret_cast<const float4*>(ep.residual + (int64_t)row * ep.ldr + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-          if constexpr (has_aux_in)
-            an[it] = ok ? *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(ep.aux_in) + (int64_t)row * ep.ld_aux + col)
-                        : make_uint2(0u, 0u);
-        }
-      };
-      prefetch(0);
+      float rscale = 1.0f;
+      if (p.row_scale != nullptr) {
+        const int row = row0 + lane;
+        rscale = row < p.M ? __ldg(p.row_scale + row / p.rows_per_scale) : 0.0f;
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(sp * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
 #pragma unroll 1
-      for (int c = 0; c < CHUNKS; ++c) {
-        const int col = cbase + c * 32 + c4 * 4;
-        if (cbase + c * 32 >= p.N) break;
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
-        float4 rc[has_res ? 8 : 1];
-        uint2 ac[has_aux_in ? 8 : 1];
-        const float4 bc = bn;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          if constexpr (has_res) rc[it] = rn[it];
-          if constexpr (has_aux_in) ac[it] = an[it];
-        }
-        tmem_ld_wait();
-        // phase 1: row-per-lane registers -> swizzled staging tile
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_a + lane * 128 + ((j ^ (lane & 7)) << 4)),
-                       "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
-                       : "memory");
-        }
-        __syncwarp();
-        if (c + 1 < CHUNKS) prefetch(c + 1);
-        // phase 2: coalesced epilogue
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + sub_r;
-          const int row = row_base + rr;
-          float4 v;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                       : "r"(stg_a + rr * 128 + ((c4 ^ (rr & 7)) << 4)));
-          if (row >= p.M || col >= p.N) continue;
-          v.x += bc.x; v.y += bc.y; v.z += bc.z; v.w += bc.w;
-          if (ep.act == UB_ACT_QUICKGELU) {
-            v.x = quick_gelu(v.x); v.y = quick_gelu(v.y); v.z = quick_gelu(v.z); v.w = quick_gelu(v.w);
-          } else if (ep.act == UB_ACT_GELU) {
-            if (ep.aux_out != nullptr) {
-              uint2 pk;
-              pk.x = pack_bf16x2(v.x, v.y); pk.y = pack_bf16x2(v.z, v.w);
-              *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.aux_out) + (int64_t)row * ep.ld_aux + col) = pk;
+      for (int c = 0; c < SLABS; ++c, ++cc) {
+        const int b = cc & 1;
+        const int col0 = slab_col(w, c);
+        // ---- staging-buffer hand-over with the TMA engine
+        if (EPI == 0) {
+          // buffer b was last read by the store issued two slabs ago (one slab ago when a pre-activation copy uses b^1)
+          if (lane == 0) {
+            if (p.has_aux_out) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+          }
+          __syncwarp();
+        } else {
+          // the store of the previous slab read buffer b^1: once done, prefetch the NEXT slab's operand into it
+          if (lane == 0) {
+            tma_store_wait_read<0>();
+            int nw = w, nc = c + 1;
+            if (nc == SLABS) { nc = 0; nw = w + w_step; }
+            if (nw < total_work) {
+              mbar_expect_tx(&rb[b ^ 1], 4096);
+              tma_load_2d(&tmR, &rb[b ^ 1], slab0 + ((b ^ 1) << 12), slab_col(nw, nc), slab_row(nw));
             }
-            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
           }
-          if constexpr (has_aux_in) {
-            const float2 a0 = unpack_bf16x2(ac[it].x), a1 = unpack_bf16x2(ac[it].y);
-            v.x *= gelu_erf_grad(a0.x); v.y *= gelu_erf_grad(a0.y); v.z *= gelu_erf_grad(a1.x); v.w *= gelu_erf_grad(a1.y);
+          __syncwarp();
+          mbar_wait(&rb[b], (cc >> 1) & 1);
+        }
+        // ---- accumulators -> registers -> epilogue math -> staging slab (row per lane, 128 B per row)
+#pragma unroll
+        for (int h = 0; h < CW / 32; ++h) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + (uint32_t)(c * CW + h * 32), r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.bias != nullptr) {
+            const float* bt = bias_tile + half * (BN / 2) + c * CW + h * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = *reinterpret_cast<const float4*>(bt + j * 4);
+              v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+            }
           }
-          if (ep.row_scale != nullptr) { v.x *= rs[it]; v.y *= rs[it]; v.z *= rs[it]; v.w *= rs[it]; }
-          if constexpr (has_res) { v.x += rc[it].x; v.y += rc[it].y; v.z += rc[it].z; v.w += rc[it].w; }
-          if (ep.out_fp32) {
-            float* out = reinterpret_cast<float*>(p.C) + (int64_t)row * p.ldc + col;
-            if (ep.accumulate) {
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+          if (EPI == 0) {
+            if (p.act == UB_ACT_QUICKGELU) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
+            } else if (p.act == UB_ACT_GELU) {
+              if (p.has_aux_out) {
+                // pre-activation copy (bf16) goes out through the other staging buffer
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t a = slab0_a + ((uint32_t)(b ^ 1) << 12) + rowoff + ((((uint32_t)(h * 4 + j)) ^ sw) << 4);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])),
+                               "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
+                               "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+                               : "memory");
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            }
+          }
+          if (EPI == 2) {
+            // multiply by gelu'(pre-activation): bf16 slab row of this lane, chunks h*4 .. h*4+3
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w)
+                           : "r"(slab0_a + ((uint32_t)b << 12) + rowoff + ((((uint32_t)(h * 4 + j)) ^ sw) << 4)));
+              const float2 a0 = unpack_bf16x2(pk.x), a1 = unpack_bf16x2(pk.y), a2 = unpack_bf16x2(pk.z), a3 = unpack_bf16x2(pk.w);
+              v[8 * j] *= gelu_erf_grad(a0.x); v[8 * j + 1] *= gelu_erf_grad(a0.y);
+              v[8 * j + 2] *= gelu_erf_grad(a1.x); v[8 * j + 3] *= gelu_erf_grad(a1.y);
+              v[8 * j + 4] *= gelu_erf_grad(a2.x); v[8 * j + 5] *= gelu_erf_grad(a2.y);
+              v[8 * j + 6] *= gelu_erf_grad(a3.x); v[8 * j + 7] *= gelu_erf_grad(a3.y);
+            }
+          }
+          if (p.row_scale != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= rscale;
+          }
+          if (OUT32) {
+            // fp32 slab: 8 chunks of 4 floats; EPI 1 adds the residual that TMA placed in the same slab
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t a = slab0_a + ((uint32_t)b << 12) + rowoff + ((((uint32_t)j) ^ sw) << 4);
+              if (EPI == 1) {
+                float4 rr;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(rr.x), "=f"(rr.y), "=f"(rr.z), "=f"(rr.w) : "r"(a));
+                v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+              }
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * j]), "f"(v[4 * j + 1]), "f"(v[4 * j + 2]),
+                           "f"(v[4 * j + 3])
                            : "memory");
-            } else {
-              *reinterpret_cast<float4*>(out) = v;
             }
           } else {
-            uint2 pk;
-            pk.x = pack_bf16x2(v.x, v.y); pk.y = pack_bf16x2(v.z, v.w);
-            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.C) + (int64_t)row * p.ldc + col) = pk;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t a = slab0_a + ((uint32_t)b << 12) + rowoff + ((((uint32_t)(h * 4 + j)) ^ sw) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[8 * j], v[8 * j + 1])),
+                           "r"(pack_bf16x2(v[8 * j + 2], v[8 * j + 3])), "r"(pack_bf16x2(v[8 * j + 4], v[8 * j + 5])),
+                           "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
+                           : "memory");
+            }
           }
         }
-        __syncwarp();   // staging tile is rewritten by the next chunk
+        // ---- hand the slab to the TMA engine
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.accumulate) tma_reduce_add_2d(&tmC, slab0 + (b << 12), col0, row0);
+          else tma_store_2d(&tmC, slab0 + (b << 12), col0, row0);
+          if (EPI == 0 && p.has_aux_out) tma_store_2d(&tmX, slab0 + ((b ^ 1) << 12), col0, row0);
+          tma_store_commit();
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -320,6 +373,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
+    if (lane == 0) tma_store_wait_read<0>();   // staging smem must stay valid until the engine has read it
   }
 
   tc_fence_before();
@@ -349,64 +403,108 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2D bf16 row-major tensor [rows, cols] with leading dimension ld (elements); box = {box_cols, box_rows}.
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols,
-                      int box_rows) {
+// 2D row-major tensor [rows, cols] of `esize`-byte elements (2: bf16, 4: fp32) with leading dimension ld (elements);
+// box = {box_cols, box_rows}, 128-byte swizzle.  Descriptors are cached: the step re-uses the same buffers every iteration.
+struct TmapKey {
+  const void* base; int64_t rows, cols, ld; int box_cols, box_rows, esize;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols && box_rows == o.box_rows &&
+           esize == o.esize;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    auto mix = [&](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix((size_t)k.rows); mix((size_t)k.cols); mix((size_t)k.ld); mix((size_t)k.box_cols * 1024 + k.box_rows * 8 + k.esize);
+    return h;
+  }
+};
+
+int make_tmap_2d(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                 int esize) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  const TmapKey key{base, rows, cols, ld, box_cols, box_rows, esize};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
   EncodeTiledFn enc = get_encode_fn();
   UB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   UB_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
-  UB_REQUIRE((ld * 2) % 16 == 0, "TMA leading dimension must be a multiple of 8 bf16 elements (ld=%lld)",
-             (long long)ld);
+  UB_REQUIRE((ld * esize) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes (ld=%lld, esize=%d)", (long long)ld, esize);
+  UB_REQUIRE(box_cols * esize == 128, "internal: TMA box must span 128 bytes per row");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  UB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld)", (int)r,
-             (long long)rows, (long long)cols, (long long)ld);
+  CUresult r = enc(out, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  UB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld box=%dx%d)", (int)r,
+             (long long)rows, (long long)cols, (long long)ld, box_cols, box_rows);
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 65536) cache.clear();
+  cache.emplace(key, *out);
   return 0;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, int NCTA>
-static int launch_gemm_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid,
-                           cudaStream_t stream) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / NCTA) * BK * 2) + 1024 + 256 + 8 * 4096;
+struct GemmMaps {
+  CUtensorMap a, b, c, r, x;
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, bool OUT32, int NCTA>
+static int launch_gemm_epi(const GemmMaps& m, const GemmParams& p, int grid, cudaStream_t stream) {
+  constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / NCTA) * BK * 2) + EPI_BYTES + 2 * BN * 4 + (2 * STAGES + 4 + 16) * 8 + 16;
   static_assert(SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
   static bool configured = false;
-  auto kern = gemm_kernel<BN, STAGES, A_MN, B_MN, EPI, NCTA>;
+  auto kern = gemm_kernel<BN, STAGES, A_MN, B_MN, EPI, OUT32, NCTA>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     UB_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(gemm smem=%d): %s", SMEM, cudaGetErrorString(e));
     configured = true;
   }
-  if (NCTA == 1) {
-    kern<<<grid, GEMM_THREADS, SMEM, stream>>>(tmA, tmB, p);
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = SMEM;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
-    UB_REQUIRE(e == cudaSuccess, "gemm_kernel (CTA-pair) launch: %s", cudaGetErrorString(e));
-  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, m.a, m.b, m.c, m.r, m.x, p);
+  UB_REQUIRE(e == cudaSuccess, "gemm_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_kernel");
 }
 
+// epilogue variants actually used per operand-major combination (keeps the kernel count down):
+//   NT   (activations x weights): every variant          NN (dgrad, B = W): bf16 out, plain or DGELU
+//   TN   (wgrad, both MN-major) : fp32 out (accumulate)
 template <int BN, int STAGES, bool A_MN, bool B_MN, int NCTA>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int grid, cudaStream_t stream) {
-  if (p.ep.residual != nullptr) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 1, NCTA>(tmA, tmB, p, grid, stream);
-  if (p.ep.act == UB_ACT_DGELU) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 2, NCTA>(tmA, tmB, p, grid, stream);
-  return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 0, NCTA>(tmA, tmB, p, grid, stream);
+static int launch_gemm(const GemmMaps& m, const GemmParams& p, int epi, bool out32, int grid, cudaStream_t stream) {
+  if constexpr (A_MN) {
+    if (epi == 0 && out32) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 0, true, NCTA>(m, p, grid, stream);
+  } else if constexpr (B_MN) {
+    if (epi == 0 && !out32) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 0, false, NCTA>(m, p, grid, stream);
+    if (epi == 2) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 2, false, NCTA>(m, p, grid, stream);
+  } else {
+    if (epi == 0 && out32) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 0, true, NCTA>(m, p, grid, stream);
+    if (epi == 0 && !out32) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 0, false, NCTA>(m, p, grid, stream);
+    if (epi == 1) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 1, true, NCTA>(m, p, grid, stream);
+    if (epi == 2) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 2, false, NCTA>(m, p, grid, stream);
+  }
+  set_error("gemm: epilogue variant (epi=%d, fp32 out=%d) is not instantiated for operand majors a_mn=%d b_mn=%d", epi, (int)out32,
+            (int)A_MN, (int)B_MN);
+  return 1;
 }
 
 }  // namespace ub
@@ -424,9 +522,13 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   UB_REQUIRE(split_k == 1 || (ep.accumulate && ep.out_fp32), "gemm: split_k>1 needs fp32 accumulate output");
   UB_REQUIRE(!ep.accumulate || ep.out_fp32, "gemm: accumulate needs fp32 output");
   UB_REQUIRE(ep.row_scale == nullptr || ep.rows_per_scale > 0, "gemm: rows_per_scale must be > 0");
-  UB_REQUIRE((ldc * (ep.out_fp32 ? 4 : 2)) % 16 == 0, "gemm: ldc must keep rows 16-byte aligned");
   UB_REQUIRE(ep.act != UB_ACT_DGELU || ep.aux_in != nullptr, "gemm: DGELU needs aux_in");
   UB_REQUIRE(!(ep.act == UB_ACT_DGELU && ep.residual != nullptr), "gemm: DGELU with a residual is not supported");
+  UB_REQUIRE(ep.residual == nullptr || ep.out_fp32, "gemm: the residual epilogue writes fp32");
+  UB_REQUIRE(ep.act != UB_ACT_DGELU || !ep.out_fp32, "gemm: the DGELU epilogue writes bf16");
+  UB_REQUIRE(ep.residual == nullptr || (ep.act == UB_ACT_NONE && !ep.accumulate),
+             "gemm: residual cannot be combined with an activation / accumulate");
+  UB_REQUIRE(ep.aux_out == nullptr || (ep.act == UB_ACT_GELU && !ep.out_fp32), "gemm: aux_out is the bf16 GELU pre-activation copy");
 
   const int total_kb = (K + BK - 1) / BK;
   if (split_k > total_kb) split_k = total_kb;
@@ -451,31 +553,42 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   if (force_ncta == 1) ncta = 1;
   if (force_ncta == 2 && bn == 256) ncta = 2;
 
-  CUtensorMap tmA, tmB;
+  const int epi = ep.residual != nullptr ? 1 : (ep.act == UB_ACT_DGELU ? 2 : 0);
+  const bool out32 = ep.out_fp32 != 0;
+  GemmMaps m;
+  memset(&m, 0, sizeof(m));
   if (a_mn_major) {
-    if (make_tmap_bf16_2d(&tmA, A, K, M, lda, 64, 64)) return 1;
+    if (make_tmap_2d(&m.a, A, K, M, lda, 64, 64, 2)) return 1;
   } else {
-    if (make_tmap_bf16_2d(&tmA, A, M, K, lda, BK, BM)) return 1;
+    if (make_tmap_2d(&m.a, A, M, K, lda, BK, BM, 2)) return 1;
   }
   if (b_mn_major) {
-    if (make_tmap_bf16_2d(&tmB, B, K, N, ldb, 64, 64)) return 1;
+    if (make_tmap_2d(&m.b, B, K, N, ldb, 64, 64, 2)) return 1;
   } else {
-    if (make_tmap_bf16_2d(&tmB, B, N, K, ldb, BK, bn / ncta)) return 1;
+    if (make_tmap_2d(&m.b, B, N, K, ldb, BK, bn / ncta, 2)) return 1;
   }
+  if (make_tmap_2d(&m.c, C, M, N, ldc, out32 ? 32 : 64, 32, out32 ? 4 : 2)) return 1;
+  m.r = m.c;
+  m.x = m.c;
+  if (epi == 1 && make_tmap_2d(&m.r, ep.residual, M, N, ep.ldr, 32, 32, 4)) return 1;
+  if (epi == 2 && make_tmap_2d(&m.r, ep.aux_in, M, N, ep.ld_aux, 64, 32, 2)) return 1;
+  if (ep.aux_out != nullptr && make_tmap_2d(&m.x, ep.aux_out, M, N, ep.ld_aux, 64, 32, 2)) return 1;
 
   GemmParams p;
-  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
-  p.splits = split_k; p.kb_per_split = kb_per_split; p.ep = ep;
+  p.M = M; p.N = N; p.K = K;
+  p.splits = split_k; p.kb_per_split = kb_per_split;
+  p.bias = ep.bias; p.row_scale = ep.row_scale; p.rows_per_scale = ep.rows_per_scale;
+  p.act = ep.act; p.accumulate = ep.accumulate; p.has_aux_out = ep.aux_out != nullptr;
   const long total_work = (long)((M + BM * ncta - 1) / (BM * ncta)) * ((N + bn - 1) / bn) * split_k;
   const int units = sms / ncta;
   const int grid = (int)(total_work < units ? total_work : units) * ncta;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
-#define UB_GEMM_CASE(AMN, BMN)                                                              \
-  if ((a_mn_major != 0) == AMN && (b_mn_major != 0) == BMN) {                                \
-    if (bn == 256 && ncta == 2) return launch_gemm<256, 6, AMN, BMN, 2>(tmA, tmB, p, grid, st); \
-    return bn == 256 ? launch_gemm<256, 4, AMN, BMN, 1>(tmA, tmB, p, grid, st)               \
-                     : launch_gemm<128, 6, AMN, BMN, 1>(tmA, tmB, p, grid, st);              \
+#define UB_GEMM_CASE(AMN, BMN)                                                                       \
+  if ((a_mn_major != 0) == AMN && (b_mn_major != 0) == BMN) {                                         \
+    if (bn == 256 && ncta == 2) return launch_gemm<256, 5, AMN, BMN, 2>(m, p, epi, out32, grid, st);  \
+    return bn == 256 ? launch_gemm<256, 3, AMN, BMN, 1>(m, p, epi, out32, grid, st)                   \
+                     : launch_gemm<128, 5, AMN, BMN, 1>(m, p, epi, out32, grid, st);                  \
   }
   UB_GEMM_CASE(false, false)
   UB_GEMM_CASE(false, true)
