@@ -91,7 +91,8 @@ UB_API int ub_teacher_embed_ln(const float* E, const float* cls, const float* po
                                float eps, float* out, int frames, int P, int D, void* stream);
 UB_API int ub_layernorm_bwd(const void* dy, const float* x, const float* gamma, float eps, const float* dx_in,
                             float* dx_out, void* dxs_out, const float* row_scale, int rows_per_scale, float* dgamma,
-                            float* dbeta, int rows, int D, void* stream);
+                            float* dbeta, float* dsum /* optional: += column sums of dxs (fp32) */, int rows, int D,
+                            void* stream);
 UB_API int ub_dec_tail_fwd(const float* y, const float* gamma, const float* beta, float eps, float* out, const float* tgt,
                            float* loss_acc, float loss_scale, int rows, int D, void* stream);
 UB_API int ub_dec_tail_bwd(const float* y, const float* gamma, const float* beta, float eps, const float* go,

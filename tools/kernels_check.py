@@ -85,7 +85,9 @@ def check_ln(rows, D):
     dx_out = torch.empty(rows, D, device=dev); dxs = torch.empty(rows, D, device=dev, dtype=torch.bfloat16)
     dg = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev)
     rs = torch.rand(rows // 16, device=dev, generator=g) + 0.5
-    ops.layernorm_bwd(dy, x, gam, 1e-6, dx_in, dx_out, dxs, rs, 16, dg, db)
+    dsum = torch.zeros(D, device=dev)
+    ops.layernorm_bwd(dy, x, gam, 1e-6, dx_in, dx_out, dxs, rs, 16, dg, db, dsum)
+    report(f"ln_bwd dsum D={D}", dsum, ((xr.grad + dx_in) * rs.repeat_interleave(16)[:, None]).sum(0), 1e-4)
     report(f"ln_bwd dx D={D}", dx_out, xr.grad + dx_in, 1e-5)
     report(f"ln_bwd dxs D={D}", dxs, (xr.grad + dx_in) * rs.repeat_interleave(16)[:, None], 4e-3)
     report(f"ln_bwd dgamma D={D}", dg, gr.grad, 1e-4)

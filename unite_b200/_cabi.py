@@ -50,7 +50,7 @@ SIGNATURES = {
     "ub_cls_attn": (C.c_int, [_P, _P, _I, _I, _I, _F, _P]),
     "ub_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P]),
     "ub_teacher_embed_ln": (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _P]),
-    "ub_layernorm_bwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P]),
+    "ub_layernorm_bwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P]),
     "ub_dec_tail_fwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _F, _I, _I, _P]),
     "ub_dec_tail_bwd": (C.c_int, [_P, _P, _P, _F, _P, _F, _P, _P, _P, _I, _I, _P]),
     "ub_l2norm_rows": (C.c_int, [_P, _I, _I, _P]),

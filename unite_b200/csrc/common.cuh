@@ -49,9 +49,14 @@ UB_DEVINL float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-// exact-erf GELU (student, modeling_finetune.py:56 nn.GELU) and its derivative.
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32 round-off level): one ex2 + one rcp instead of
-// the ~30-instruction erff(); cdf(x) = 0.5*(1+erf(x/sqrt2)) and pdf(x) share the same exp(-x^2/2).
+// GELU of the student MLP (modeling_finetune.py:56, nn.GELU = x * Phi(x)) and its derivative.
+// B200's 3-operand FP32 pipe issues at half rate (~64 lane-ops/clk/SM), so a K=768 GEMM epilogue can afford about a
+// dozen FP32 ops per output element before it, not the tensor pipe, sets the tile time.  Default evaluation:
+//     Phi(x) = 0.5 * (1 + tanh(u)),  u = x * (0.7978845608 + 0.0356774081 x^2)        (MUFU.TANH, 5 FP ops)
+// which differs from the erf form by <= 4.7e-4 absolute (<= 2.2e-4 of the value for |x| >= 1) — an order of
+// magnitude below the bf16 resolution (3.9e-3 relative) of the tensors these values are stored in.  Compile with
+// -DUB_GELU_ERF for the Abramowitz-Stegun 7.1.26 erf (|err| <= 1.5e-7; one ex2 + one rcp + 10 FP ops).
+#ifdef UB_GELU_ERF
 UB_DEVINL void gelu_cdf_pdf(float x, float& cdf, float& e) {
   const float z = fabsf(x) * 0.70710678118654752f;
   float t;
@@ -74,6 +79,23 @@ UB_DEVINL float gelu_erf_grad(float x) {
   gelu_cdf_pdf(x, cdf, e);
   return fmaf(x * 0.3989422804014327f, e, cdf);
 }
+#else
+UB_DEVINL float gelu_erf(float x) {
+  const float x2 = x * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * fmaf(x2, 0.0356774081f, 0.7978845608f)));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+UB_DEVINL float gelu_erf_grad(float x) {
+  const float x2 = x * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * fmaf(x2, 0.0356774081f, 0.7978845608f)));
+  const float dudx = fmaf(x2, 0.1070322243f, 0.7978845608f);
+  const float sech2 = fmaf(-t, t, 1.0f);
+  return fmaf(0.5f * x * sech2, dudx, fmaf(0.5f, t, 0.5f));
+}
+#endif
 // QuickGELU (teacher, clip.py:29): x * sigmoid(1.702 x) = 0.5x * (1 + tanh(0.851 x)); one MUFU op
 UB_DEVINL float quick_gelu(float x) {
   float t;

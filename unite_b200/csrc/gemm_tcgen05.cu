@@ -542,14 +542,18 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
     const char* e = getenv("UB_GEMM_NCTA");
     force_ncta = e ? atoi(e) : 0;
   }
-  auto cost = [&](int bm, int bn, int units) {
+  // estimated time ~ waves x per-SM tile area / efficiency of the configuration (measured on B200: the 256-wide CTA-pair
+  // tile has twice the operand reuse of the 128-wide tile and sustains ~1.3 PF; 1-CTA 256-wide ~1.15 PF; 128-wide ~0.75 PF)
+  auto cost = [&](int bm, int bn, int units, double eff) {
     const long tiles = (long)((M + bm - 1) / bm) * ((N + bn - 1) / bn) * split_k;
     const long waves = (tiles + units - 1) / units;
-    return waves * (long)bm * bn / (bm / BM);   // time ~ per-SM tile area x waves
+    return (double)waves * (double)BM * bn / eff;
   };
-  const int bn = (N <= 128 || cost(BM, 128, sms) < cost(BM, 256, sms)) ? 128 : 256;
-  int ncta = 1;
-  if (bn == 256 && M > BM) ncta = (cost(2 * BM, 256, sms / 2) <= cost(BM, 256, sms)) ? 2 : 1;
+  const double c128 = cost(BM, 128, sms, 0.58), c256 = cost(BM, 256, sms, 0.88);
+  const double c256x2 = M > BM ? cost(2 * BM, 256, sms / 2, 1.0) : 1e30;
+  int bn = 256, ncta = 1;
+  if (N <= 128 || (c128 < c256 && c128 < c256x2)) bn = 128;
+  else if (c256x2 <= c256) ncta = 2;
   if (force_ncta == 1) ncta = 1;
   if (force_ncta == 2 && bn == 256) ncta = 2;
 

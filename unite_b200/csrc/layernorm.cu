@@ -185,6 +185,7 @@ struct LnBwdArgs {
   int rows_per_scale;
   float* dgamma;
   float* dbeta;
+  float* dsum;              // optional: += sum_rows dx_out * row_scale  (bias gradient of the Linear that consumes dxs)
   int rows, D;
   float eps;
 };
@@ -209,11 +210,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
   const int lane = threadIdx.x & 31;
   constexpr int nv = NV;
   const int wpb = blockDim.x >> 5;
-  RowT<NV> g, dgam, dbet;
-  row_load_f32(g, a.gamma, nv, lane);
+  RowT<NV> dgam, dbet, dsm;
   UB_ROW_FOREACH(i, nv) {
     dgam.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     dbet.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    dsm.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float invD = 1.f / (float)a.D;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < a.rows; row += gridDim.x * wpb) {
@@ -228,7 +229,9 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
       dgam.v[i].x += dy.v[i].x * x.v[i].x; dgam.v[i].y += dy.v[i].y * x.v[i].y;
       dgam.v[i].z += dy.v[i].z * x.v[i].z; dgam.v[i].w += dy.v[i].w * x.v[i].w;
       dbet.v[i].x += dy.v[i].x; dbet.v[i].y += dy.v[i].y; dbet.v[i].z += dy.v[i].z; dbet.v[i].w += dy.v[i].w;
-      dy.v[i].x *= g.v[i].x; dy.v[i].y *= g.v[i].y; dy.v[i].z *= g.v[i].z; dy.v[i].w *= g.v[i].w;
+      float4 g;   // gamma from L1 per row (keeps 4*NV registers free for the extra accumulators)
+      asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "l"(a.gamma + (i * 32 + lane) * 4));
+      dy.v[i].x *= g.x; dy.v[i].y *= g.y; dy.v[i].z *= g.z; dy.v[i].w *= g.w;
       s1 += (dy.v[i].x + dy.v[i].y) + (dy.v[i].z + dy.v[i].w);
       s2 += dy.v[i].x * x.v[i].x + dy.v[i].y * x.v[i].y + dy.v[i].z * x.v[i].z + dy.v[i].w * x.v[i].w;
     }
@@ -246,12 +249,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
     row_store_f32(dx, a.dx_out + (int64_t)row * a.D, nv, lane);
     if (a.dxs_out) {
       const float sc = a.row_scale ? __ldg(a.row_scale + row / a.rows_per_scale) : 1.0f;
-      UB_ROW_FOREACH(i, nv) { dx.v[i].x *= sc; dx.v[i].y *= sc; dx.v[i].z *= sc; dx.v[i].w *= sc; }
+      UB_ROW_FOREACH(i, nv) {
+        dx.v[i].x *= sc; dx.v[i].y *= sc; dx.v[i].z *= sc; dx.v[i].w *= sc;
+        dsm.v[i].x += dx.v[i].x; dsm.v[i].y += dx.v[i].y; dsm.v[i].z += dx.v[i].z; dsm.v[i].w += dx.v[i].w;
+      }
       row_store_bf16(dx, a.dxs_out + (int64_t)row * a.D, nv, lane);
     }
   }
   block_col_reduce_atomic(dgam, s_red, a.dgamma, nv, a.D);
   block_col_reduce_atomic(dbet, s_red, a.dbeta, nv, a.D);
+  if (a.dsum != nullptr) block_col_reduce_atomic(dsm, s_red, a.dsum, nv, a.D);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -424,11 +431,12 @@ extern "C" int ub_teacher_embed_ln(const float* E, const float* cls, const float
 
 extern "C" int ub_layernorm_bwd(const void* dy, const float* x, const float* gamma, float eps, const float* dx_in,
                                 float* dx_out, void* dxs_out, const float* row_scale, int rows_per_scale, float* dgamma,
-                                float* dbeta, int rows, int D, void* stream) {
+                                float* dbeta, float* dsum, int rows, int D, void* stream) {
   UB_REQUIRE(dy && x && gamma && dx_out && dgamma && dbeta, "layernorm_bwd: null pointer");
   UB_REQUIRE(row_scale == nullptr || rows_per_scale > 0, "layernorm_bwd: rows_per_scale must be > 0");
+  UB_REQUIRE(dsum == nullptr || dxs_out != nullptr, "layernorm_bwd: dsum is the column sum of dxs_out");
   if (check_D(D, "layernorm_bwd")) return 1;
-  LnBwdArgs a{(const bf16*)dy, x, gamma, dx_in, dx_out, (bf16*)dxs_out, row_scale, rows_per_scale, dgamma, dbeta, rows, D, eps};
+  LnBwdArgs a{(const bf16*)dy, x, gamma, dx_in, dx_out, (bf16*)dxs_out, row_scale, rows_per_scale, dgamma, dbeta, dsum, rows, D, eps};
   UB_LN_DISPATCH(D, ln_bwd_kernel, ln_bwd_grid(rows), 8 * D * sizeof(float), (cudaStream_t)stream, a)
   return check_launch("ln_bwd_kernel");
 }

@@ -309,11 +309,11 @@ class AdaptationCore:
         N = state["Nv"]
 
         def make_tap(l, grads):
-            def tap(dx_in, dxs_out, row_scale):
+            def tap(dx_in, dxs_out, row_scale, dsum):
                 for i, dz in enumerate(grads):
                     last = i == len(grads) - 1
                     ops.layernorm_bwd(dz, ws.x_at(l + 1), enc_w, self.eps, dx_in, ws.dx, dxs_out if last else None,
-                                      row_scale, N, g_enc_w, g_enc_b)
+                                      row_scale, N, g_enc_w, g_enc_b, dsum=dsum if last else None)
                     dx_in = ws.dx
             return tap
 

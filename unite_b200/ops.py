@@ -139,11 +139,12 @@ def teacher_embed_ln(E, cls, pos, gamma, beta, eps, out, frames, P, D):
 
 
 @_instrument("layernorm_bwd", 1)
-def layernorm_bwd(dy, x, gamma, eps, dx_in, dx_out, dxs_out, row_scale, rows_per_scale, dgamma, dbeta):
+def layernorm_bwd(dy, x, gamma, eps, dx_in, dx_out, dxs_out, row_scale, rows_per_scale, dgamma, dbeta, dsum=None):
     rows, D = x.shape
     check(lib.ub_layernorm_bwd(_p(dy, BF16, "dy"), _p(x, F32, "x"), _p(gamma, F32, "gamma"), eps, _p(dx_in, F32, "dx_in"),
                                _p(dx_out, F32, "dx_out"), _p(dxs_out, BF16, "dxs_out"), _p(row_scale, F32, "row_scale"),
-                               rows_per_scale, _p(dgamma, F32, "dgamma"), _p(dbeta, F32, "dbeta"), rows, D, _stream()),
+                               rows_per_scale, _p(dgamma, F32, "dgamma"), _p(dbeta, F32, "dbeta"), _p(dsum, F32, "dsum"), rows, D,
+                               _stream()),
           "ub_layernorm_bwd")
 
 

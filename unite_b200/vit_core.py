@@ -150,9 +150,9 @@ class ViTTrunk:
     def backward(self, ws: TrunkWorkspace, tap_grads: Dict[int, callable], dx_init: bool = False, on_block_done=None):
         """Back-propagates through blocks n_layers-1 .. 0 and the patch embedding.
 
-        tap_grads[l](dx_in, dxs_out, row_scale) must add the gradient arriving at the OUTPUT of block l into the
-        residual-gradient buffer ws.dx (dx_in is None when nothing has been accumulated yet) and emit
-        ws.dxs = bf16(ws.dx * row_scale).  If dx_init is True, ws.dx already holds the gradient wrt the last
+        tap_grads[l](dx_in, dxs_out, row_scale, dsum) must add the gradient arriving at the OUTPUT of block l into the
+        residual-gradient buffer ws.dx (dx_in is None when nothing has been accumulated yet), emit
+        ws.dxs = bf16(ws.dx * row_scale) and accumulate its column sums (block l's fc2 bias gradient) into dsum.  If dx_init is True, ws.dx already holds the gradient wrt the last
         block's output."""
         N, D = ws.N, self.D
         dp = ws.dp
@@ -163,25 +163,25 @@ class ViTTrunk:
             b = f"blocks.{l}."
             s_mlp = None if dp is None else dp[l, 1]
             s_att = None if dp is None else dp[l, 0]
+            # the producer of ws.dxs also accumulates its column sums = the bias gradient of the Linear it feeds
             if l in tap_grads:
-                tap_grads[l](ws.dx if have_dx else None, ws.dxs, s_mlp)
+                tap_grads[l](ws.dx if have_dx else None, ws.dxs, s_mlp, self.g(b + "mlp.fc2.bias"))
                 have_dx = True
             elif l == nl - 1:
                 assert have_dx, "no gradient reaches the last block"
                 ops.cast_scale_bf16(ws.dx, ws.dxs, s_mlp, N)
+                ops.colsum_bf16(ws.dxs, self.g(b + "mlp.fc2.bias"))
             # ---- MLP branch: x_out = x_mid + s * (gelu(h2 W1^T + b1) W2^T + b2)
             ops.gemm(ws.dxs, self.w(b + "mlp.fc2.weight"), ws.d_pre, b_t=True, act=ops.UB_ACT_DGELU, aux_in=L.pre)
             self._wgrad(ws.dxs, L.act, self.g(b + "mlp.fc2.weight"))
-            ops.colsum_bf16(ws.dxs, self.g(b + "mlp.fc2.bias"))
             ops.gemm(ws.d_pre, self.w(b + "mlp.fc1.weight"), ws.d_h, b_t=True)
             self._wgrad(ws.d_pre, L.h2, self.g(b + "mlp.fc1.weight"))
             ops.colsum_bf16(ws.d_pre, self.g(b + "mlp.fc1.bias"))
             ops.layernorm_bwd(ws.d_h, L.x_mid, self.p(b + "norm2.weight"), self.eps, ws.dx, ws.dx, ws.dxs, s_att, N,
-                              self.g(b + "norm2.weight"), self.g(b + "norm2.bias"))
+                              self.g(b + "norm2.weight"), self.g(b + "norm2.bias"), dsum=self.g(b + "attn.proj.bias"))
             # ---- attention branch: x_mid = x_in + s * (attn(h1) Wp^T + bp)
             ops.gemm(ws.dxs, self.w(b + "attn.proj.weight"), ws.d_o, b_t=True)
             self._wgrad(ws.dxs, L.o, self.g(b + "attn.proj.weight"))
-            ops.colsum_bf16(ws.dxs, self.g(b + "attn.proj.bias"))
             ops.attn_bwd(L.qkv, L.o, ws.d_o, L.lse, ws.d_ws, ws.dqkv, ws.B, N, self.H, self.scale)
             ops.gemm(ws.dqkv, self.w(b + "attn.qkv.weight"), ws.d_h, b_t=True)
             self._wgrad(ws.dqkv, L.h1, self.g(b + "attn.qkv.weight"))
@@ -190,11 +190,12 @@ class ViTTrunk:
             # next consumer of dxs: block l-1's MLP branch (unless a tap re-emits it) or the patch embedding
             emit = (l - 1) not in tap_grads
             s_next = None if (dp is None or l == 0) else dp[l - 1, 1]
+            next_bias = self.g("patch_embed.proj.bias") if l == 0 else self.g(f"blocks.{l - 1}.mlp.fc2.bias")
             ops.layernorm_bwd(ws.d_h, ws.x_at(l), self.p(b + "norm1.weight"), self.eps, ws.dx, ws.dx,
-                              ws.dxs if emit else None, s_next, N, self.g(b + "norm1.weight"), self.g(b + "norm1.bias"))
+                              ws.dxs if emit else None, s_next, N, self.g(b + "norm1.weight"), self.g(b + "norm1.bias"),
+                              dsum=next_bias if emit else None)
             if on_block_done is not None:
                 on_block_done(l)     # every gradient of block l is final: its arena range can be all-reduced
         # ---- patch embedding (Conv3d as GEMM): only weight and bias gradients exist
         gw = self.g("patch_embed.proj.weight")
         self._wgrad(ws.dxs, ws.patches, gw.view(D, -1))
-        ops.colsum_bf16(ws.dxs, self.g("patch_embed.proj.bias"))
