@@ -54,6 +54,15 @@ def check_attention(n_seq, S, H, time_it=False):
     att = torch.empty(n_seq, S - 1, device=dev)
     ops.cls_attn(qkv, att, n_seq, S, H, scale)
     report(f"cls_attn     S={S} H={H}", att, p.mean(1)[:, 0, 1:], 3e-3)
+    if S <= 240:
+        o2 = torch.full_like(o, float("nan"))
+        ops.attn_fwd(qkv, o2, None, n_seq, S, H, scale)       # tcgen05 / TMEM inference kernel (no LSE)
+        torch.cuda.synchronize()
+        report(f"attn_fwd_tc  S={S} H={H}", o2.view(n_seq, S, H, 64).permute(0, 2, 1, 3), oref.detach(), 6e-3)
+        if time_it:
+            fl = 4 * S * S * 64 * H * n_seq
+            t = timeit(lambda: ops.attn_fwd(qkv, o2, None, n_seq, S, H, scale))
+            print(f"   attn fwd (tcgen05) {t*1e3:.0f} us ({fl/t/1e9:.0f} TF/s)")
     if time_it:
         fl = 4 * S * S * 64 * H * n_seq
         t = timeit(lambda: ops.attn_fwd(qkv, o, lse, n_seq, S, H, scale))
@@ -198,7 +207,11 @@ if __name__ == "__main__":
     check_ln(4096, 768); check_ln(1024, 128); check_ln(512, 1024)
     check_dec_tail(4096, 512); check_dec_tail(300, 128)
     check_optim()
+    check_attention(2, 17, 2)
     check_attention(4, 197, 12)
+    check_attention(3, 128, 4)
+    check_attention(5, 240, 3)
+    check_attention(2, 256, 3)
     check_attention(3, 320, 12)
     check_attention(2, 64, 2)
     check_attention(1, 1568, 4)

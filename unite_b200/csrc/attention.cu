@@ -11,6 +11,7 @@
 // cp.async double buffering; attention is ~5% of the step FLOPs, the tcgen05 budget went
 // to the GEMMs first.
 #include "common.cuh"
+#include <cstdlib>
 #include "../../include/unite_b200.h"
 
 namespace ub {
@@ -539,12 +540,23 @@ __global__ void cls_attn_kernel(const bf16* __restrict__ qkv, float* __restrict_
 
 }  // namespace ub
 
+namespace ub {
+int launch_attn_fwd_tc(const void* qkv, void* o, int n_seq, int S, int H, float scale, cudaStream_t stream);
+}
 using namespace ub;
 
 extern "C" int ub_attn_fwd(const void* qkv, void* o, float* lse, int n_seq, int S, int H, float scale, void* stream) {
   UB_REQUIRE(qkv && o, "attn_fwd: null pointer");
   UB_REQUIRE(n_seq > 0 && S > 0 && H > 0, "attn_fwd: bad shape n_seq=%d S=%d H=%d", n_seq, S, H);
   UB_REQUIRE(n_seq <= 65535 && H <= 65535, "attn_fwd: grid too large");
+  // inference over short sequences (the teacher's 197-token frames): tcgen05 / TMEM kernel
+  static int use_tc = -1;
+  if (use_tc < 0) {
+    const char* e = getenv("UB_ATTN_TC");
+    use_tc = e ? atoi(e) : 1;
+  }
+  if (use_tc && lse == nullptr && S <= 240) return   // (K and V for NK <= 240 padded keys fit the 227 KB smem budget twice)
+    launch_attn_fwd_tc(qkv, o, n_seq, S, H, scale, (cudaStream_t)stream);
   dim3 grid((S + TQ - 1) / TQ, H, n_seq);
   attn_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)o, lse, S, H, scale);
   return check_launch("attn_fwd_kernel");
