@@ -164,8 +164,21 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path in unite_b200); use --impl reference for the CPU oracle")
-    rank, local, world = init_distributed_from_env()
-    dev = torch.device("cuda", local)
+    # NCCL prints its version banner on stdout when the communicator is created; the driver wants ONE JSON line there
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, local, world = init_distributed_from_env()
+        dev = torch.device("cuda", local)
+        if world > 1:
+            warm = torch.ones(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
     B = args.batch
     student, teacher = build_models(seed=0)                       # identical weights on every rank (DDP broadcast equivalent)
     student, teacher = student.to(dev).train(), teacher.to(dev).eval()
