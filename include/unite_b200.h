@@ -129,6 +129,30 @@ UB_API int ub_adamw(float* p, const float* g, float* m, float* v, void* w_bf16 /
                     void* stream);
 UB_API int ub_cast_bf16(const float* x, void* out, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Classification heads and stage-3 pseudo-label fusion (fp32, small).
+ *   ub_meanpool_fwd/bwd      x.mean(1): modeling_finetune.py:374-376 (stage 2), run_stage3.py:333-338 pool_outputs
+ *   ub_linear_small_fwd/bwd  few-output Linear: `head` (modeling_finetune.py:382), `src_classifier` (run_stage3.py:1193);
+ *                            bwd ACCUMULATES dW / db, dx optional
+ *   ub_softmax_ce            loss_acc += scale * sum_b w_b CE(logits_b, y_b); dlogits = its gradient
+ *                            (engine_for_finetuning.py:39; run_stage3.py:486, 606-615)
+ *   ub_clip_zero_shot        utils.py:62-68: per-frame softmax(100 * cosine) averaged over the T frames of a clip
+ *   ub_pseudo_label_fusion   run_stage3.py:489-490,556-587 ('clip_matchORconf'): msp / argmax of the student, selection
+ *                            mask, pseudo labels (= student argmax, :576) and per-sample loss weights
+ * ---------------------------------------------------------------------------------------------- */
+UB_API int ub_meanpool_fwd(const float* x, float* out, int B, int N, int D, void* stream);
+UB_API int ub_meanpool_bwd(const float* g, float* dx, int B, int N, int D, void* stream);
+UB_API int ub_linear_small_fwd(const float* x, const float* W, const float* bias, float* out, int B, int C, int D,
+                               void* stream);
+UB_API int ub_linear_small_bwd(const float* x, const float* W, const float* dout, float* dx, float* dW, float* db, int B,
+                               int C, int D, void* stream);
+UB_API int ub_softmax_ce(const float* logits, const int* labels, const float* weights, float scale, float* loss_acc,
+                         float* dlogits, int B, int C, void* stream);
+UB_API int ub_clip_zero_shot(const float* img_feat, const float* text_feat, float* probs, int B, int T, int C, int D,
+                             void* stream);
+UB_API int ub_pseudo_label_fusion(const float* logits_full, const float* clip_probs, float threshold, int conf_weighted,
+                                  float* msp, int* pseudo, uint8_t* sel, float* weight, int B, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,7 +107,7 @@ def _ln(x: Tensor, w: Tensor, b: Tensor, eps: float) -> Tensor:
 # --------------------------------------------------------------------------------------------------
 # teacher: CLIP ViT  (clip.py)
 # --------------------------------------------------------------------------------------------------
-def teacher_forward(sd: SD, x: Tensor, cfg: TeacherCfg):
+def teacher_forward(sd: SD, x: Tensor, cfg: TeacherCfg, return_cls: bool = False):
     """clip.VisionTransformer.forward with return_attn=True, mask=None (clip.py:145-188).
 
     Returns (feat [K,B,T'*HW,C_out] L2-normalised, attn [B*T', HW]) with T' = T / kernel_size.
@@ -153,6 +153,10 @@ def teacher_forward(sd: SD, x: Tensor, cfg: TeacherCfg):
     z = _ln(z[:, :, 1:, :], sd["ln_post.weight"], sd["ln_post.bias"], cfg.ln_eps)
     z = z.reshape(K, B, Tp * HW, D) @ sd["proj"]
     z = z / z.norm(dim=-1, keepdim=True)
+    if return_cls:
+        # image embedding of OpenAI CLIP's encode_image: ln_post(CLS of the last block) @ proj (then L2-normalised by clip_infer)
+        c = _ln(h[:, 0, :], sd["ln_post.weight"], sd["ln_post.bias"], cfg.ln_eps) @ sd["proj"]
+        return z, attn_cls, c / c.norm(dim=-1, keepdim=True)
     return z, attn_cls
 
 
@@ -369,3 +373,39 @@ def pseudo_label_fusion(logits_full_t: Tensor, logits_masked_t: Tensor, clip_pro
     else:
         loss_t = torch.zeros(())
     return dict(sel_mask=sel, pseudo=pseudo, msp=msp, match=match, conf=conf, loss_t=loss_t)
+
+
+def stage3_step(student_sd: SD, teacher_sd: SD, cls_w: Tensor, cls_b: Tensor, text_features: Tensor, videos_s: Tensor,
+                labels_s: Tensor, videos_t: Tensor, scfg: StudentCfg, tcfg: TeacherCfg, mask_ratio: float = 0.8, k: int = 2,
+                clip_threshold: float = 0.5, src_ratio: float = 1.0, tgt_ratio: float = 1.0, with_grads: bool = True):
+    """Collaborative self-training step, masking_type='clip_attention', selection_strategy='clip_matchORconf',
+    train_masked=True, conf_weighted_loss=True (run_stage3.py:427-642).  The OpenAI-CLIP zero-shot tower (absent here) is
+    replaced by the teacher trunk's CLS embedding and the given text matrix; src_classifier is frozen (run_stage3.py:1193,1264)."""
+    Bs, Bt = videos_s.shape[0], videos_t.shape[0]
+    with torch.no_grad():
+        _, attn, img = teacher_forward(teacher_sd, videos_t, tcfg, return_cls=True)            # :434-451 (attn only is used)
+    params = {k_: v.detach().clone().requires_grad_(with_grads) for k_, v in student_sd.items()}
+    full_s = torch.zeros(Bs, scfg.num_patches, dtype=torch.bool)
+    full_t = torch.zeros(Bt, scfg.num_patches, dtype=torch.bool)
+    enc_s, _ = student_forward(params, videos_s, full_s, scfg, clip_only=False)                 # :475
+    logits_s = F.linear(pool_outputs(enc_s), cls_w, cls_b)                                      # :476-477
+    with torch.no_grad():
+        enc_t, _ = student_forward(params, videos_t, full_t, scfg, clip_only=False)             # :480-481
+        logits_full_t = F.linear(pool_outputs(enc_t), cls_w, cls_b)                             # :482-483
+    loss_s = F.cross_entropy(logits_s, labels_s)                                                # :486
+    gm = greedy_masks(attn, mask_ratio, k)                                                      # :496
+    T = attn.shape[0] // Bt
+    masks = gm.reshape(k, Bt, T * attn.shape[1]).reshape(k * Bt, -1)                            # 'k (B T) N -> (k B) (T N)'  :497
+    videos_tk = videos_t.repeat(k, 1, 1, 1, 1)                                                  # :499
+    enc_m, _ = student_forward(params, videos_tk, masks, scfg, clip_only=False)                 # :502
+    logits_masked = F.linear(pool_outputs(enc_m), cls_w, cls_b).reshape(k, Bt, -1)              # :503-505
+    clip_probs = clip_zero_shot(img, text_features, Bt)                                         # :557
+    fus = pseudo_label_fusion(logits_full_t, logits_masked, clip_probs, clip_threshold, tgt_ratio)
+    loss = src_ratio * loss_s + fus["loss_t"]                                                   # :625
+    res = dict(attn=attn, masks=gm, logits_s=logits_s.detach(), logits_full_t=logits_full_t, logits_masked=logits_masked.detach(),
+               clip_probs=clip_probs, sel_mask=fus["sel_mask"], pseudo=fus["pseudo"], msp=fus["msp"], loss_s=loss_s.detach(),
+               loss_t=fus["loss_t"].detach(), loss=loss.detach())
+    if with_grads:
+        loss.backward()
+        res["grads"] = {k_: v.grad for k_, v in params.items() if v.grad is not None}
+    return res

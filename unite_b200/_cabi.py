@@ -62,6 +62,13 @@ SIGNATURES = {
     "ub_sumsq": (C.c_int, [_P, _L, _P, _P]),
     "ub_adamw": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
     "ub_cast_bf16": (C.c_int, [_P, _P, _L, _P]),
+    "ub_meanpool_fwd": (C.c_int, [_P, _P, _I, _I, _I, _P]),
+    "ub_meanpool_bwd": (C.c_int, [_P, _P, _I, _I, _I, _P]),
+    "ub_linear_small_fwd": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "ub_linear_small_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "ub_softmax_ce": (C.c_int, [_P, _P, _P, _F, _P, _P, _I, _I, _P]),
+    "ub_clip_zero_shot": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "ub_pseudo_label_fusion": (C.c_int, [_P, _P, _F, _I, _P, _P, _P, _P, _I, _I, _P]),
 }
 
 

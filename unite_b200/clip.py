@@ -153,6 +153,7 @@ class VisionTransformer(nn.Module):
             cur = dst
             if i in ret:
                 keep.append(cur)
+        self.last_stream = cur        # residual stream after the final block (CLS rows feed the stage-3 zero-shot head)
         return keep, attn, patches
 
     @torch.no_grad()
@@ -170,6 +171,15 @@ class VisionTransformer(nn.Module):
         ops.gemm(z, w["proj_t"], out)
         ops.l2norm_rows(out)
         return out.view(K, n, self.output_dim)
+
+    @torch.no_grad()
+    def cls_features(self, frames: int, P: int) -> torch.Tensor:
+        """ln_post(CLS) @ proj, L2-normalised, of the last forward_features call: fp32 [frames, output_dim] — the image
+        embedding OpenAI CLIP's encode_image returns (stand-in for the stage-3 zero-shot tower, utils.py:55-68)."""
+        key = ("cls_rows", frames, P)
+        if key not in self._bufs:
+            self._bufs[key] = (torch.arange(frames, device=self.proj.device) * (P + 1)).to(I32).contiguous()
+        return self.project_rows([self.last_stream], self._bufs[key])[0]
 
     def _all_patch_rows(self, B, Tp, P, dev):
         key = ("rows", B, Tp, P)

@@ -231,13 +231,14 @@ class AdaptationCore:
             if save:
                 d["dy"] = torch.empty(M, self.C, device=dev, dtype=BF16)
                 d["dz"] = torch.empty(K, M, self.D, device=dev, dtype=BF16)
-                d["gv"] = torch.empty(M, self.D, device=dev, dtype=BF16)
             self._dec_ws[key] = d
         return self._dec_ws[key]
 
-    def run_forward(self, x, vis_idx, patches, dp, clip_only, save, targets=None, loss_acc=None):
-        """Returns (x_vis or None, x_clip [K,B,Nv,C] fp32, state).  With `targets` ([K,B,Nv,C] fp32) the decoder
-        tail also accumulates the alignment loss mean(2 - 2<out,tgt>) into loss_acc (fp32 [1])."""
+    def run_forward(self, x, vis_idx, patches, dp, clip_only, save, targets=None, loss_acc=None, want_clip=True, abs_rows=None):
+        """Returns (x_vis or None, x_clip [K,B,Nv,C] fp32 or None, state).  With `targets` ([K,B,Nv,C] fp32) the decoder
+        tail also accumulates the alignment loss mean(2 - 2<out,tgt>) into loss_acc (fp32 [1]).
+        want_clip=False skips the alignment decoders (stage 3 only uses the encoder output, run_stage3.py:475-483);
+        abs_rows int32 [B*Nv]: absolute rows of `patches` to gather (committee members share one clip's patches)."""
         self.sync_shadow()
         B = x.shape[0]
         Nv = vis_idx.shape[1]
@@ -248,20 +249,23 @@ class AdaptationCore:
             patches = torch.empty(B * self.N, 3 * self.tubelet * 256, device=dev, dtype=BF16)
             ops.patchify(x.contiguous(), patches, self.tubelet)
         p_vis = torch.empty(M, patches.shape[1], device=dev, dtype=BF16)
-        ops.gather_rows(patches, vis_flat, p_vis, rows_per_group=Nv, group_stride_rows=self.N)
+        if abs_rows is not None:
+            ops.gather_rows(patches, abs_rows, p_vis)
+        else:
+            ops.gather_rows(patches, vis_flat, p_vis, rows_per_group=Nv, group_stride_rows=self.N)
         pos_vis = torch.empty(M, self.D, device=dev, dtype=F32)
         ops.gather_rows(self.pos, vis_flat, pos_vis)
         n_layers = (max(self.taps) + 1) if clip_only else self.depth
         K = len(self.taps)
-        dws = self._decoder_bufs(M, save)
-        out = torch.empty(K, M, self.C, device=dev, dtype=F32)
+        dws = self._decoder_bufs(M, save) if want_clip else None
+        out = torch.empty(K, M, self.C, device=dev, dtype=F32) if want_clip else None
         a = self.arena
         enc_w, enc_b = a.p32("encoder.norm.weight"), a.p32("encoder.norm.bias")
         tap_of = {l: k for k, l in enumerate(self.taps)}
         loss_scale = 1.0 / (K * M)
 
         def after_layer(l, x_l):
-            if l not in tap_of:
+            if l not in tap_of or not want_clip:
                 return
             k = tap_of[l]
             z = dws["z"][k if save else 0]
@@ -278,7 +282,7 @@ class AdaptationCore:
             ops.layernorm_fwd(ws.x_at(self.depth), enc_w, enc_b, self.eps, x_vis)
             x_vis = x_vis.view(B, Nv, self.D)
         state = dict(ws=ws, dws=dws, B=B, Nv=Nv, M=M, vis_flat=vis_flat, clip_only=clip_only) if save else None
-        return x_vis, out.view(K, B, Nv, self.C), state
+        return x_vis, (out.view(K, B, Nv, self.C) if want_clip else None), state
 
     def block_grad_hi(self, l):
         """End of the decay-segment prefix that is final once block l's backward has run (decoders + blocks >= l)."""
@@ -323,8 +327,9 @@ class AdaptationCore:
                 if l < ws.n_layers:
                     per_layer.setdefault(l, []).append(dws["dz"][k])
         if g_vis is not None:
-            ops.cast_scale_bf16(g_vis.reshape(M, self.D).contiguous().float(), dws["gv"])
-            per_layer.setdefault(self.depth - 1, []).append(dws["gv"])
+            gv = torch.empty(M, self.D, device=a.device, dtype=BF16)
+            ops.cast_scale_bf16(g_vis.reshape(M, self.D).contiguous().float(), gv)
+            per_layer.setdefault(self.depth - 1, []).append(gv)
         for l, grads in per_layer.items():
             taps[l] = make_tap(l, grads)
         if (ws.n_layers - 1) not in taps:

@@ -222,3 +222,58 @@ def adamw(p, g, m, v, w16, n_decay, lr, wd, beta1, beta2, eps, step, grad_scale=
 @_instrument("cast_bf16", 1)
 def cast_bf16(x, out):
     check(lib.ub_cast_bf16(_p(x, F32, "x"), _p(out, BF16, "out"), x.numel(), _stream()), "ub_cast_bf16")
+
+
+@_instrument("meanpool_fwd", 1)
+def meanpool_fwd(x, out):
+    B, N, D = x.shape
+    check(lib.ub_meanpool_fwd(_p(x, F32, "x"), _p(out, F32, "out"), B, N, D, _stream()), "ub_meanpool_fwd")
+    return out
+
+
+@_instrument("meanpool_bwd", 1)
+def meanpool_bwd(g, dx):
+    B, N, D = dx.shape
+    check(lib.ub_meanpool_bwd(_p(g, F32, "g"), _p(dx, F32, "dx"), B, N, D, _stream()), "ub_meanpool_bwd")
+    return dx
+
+
+@_instrument("linear_small_fwd", 1)
+def linear_small_fwd(x, W, bias, out):
+    B, D = x.shape
+    Cc = W.shape[0]
+    check(lib.ub_linear_small_fwd(_p(x, F32, "x"), _p(W, F32, "W"), _p(bias, F32, "bias"), _p(out, F32, "out"), B, Cc, D, _stream()),
+          "ub_linear_small_fwd")
+    return out
+
+
+@_instrument("linear_small_bwd", 1)
+def linear_small_bwd(x, W, dout, dx, dW, db):
+    B, D = x.shape
+    Cc = W.shape[0]
+    check(lib.ub_linear_small_bwd(_p(x, F32, "x"), _p(W, F32, "W"), _p(dout, F32, "dout"), _p(dx, F32, "dx"), _p(dW, F32, "dW"),
+                                  _p(db, F32, "db"), B, Cc, D, _stream()), "ub_linear_small_bwd")
+
+
+@_instrument("softmax_ce", 1)
+def softmax_ce(logits, labels, weights, scale, loss_acc, dlogits):
+    B, Cc = logits.shape
+    check(lib.ub_softmax_ce(_p(logits, F32, "logits"), _p(labels, I32, "labels"), _p(weights, F32, "weights"), scale,
+                            _p(loss_acc, F32, "loss_acc"), _p(dlogits, F32, "dlogits"), B, Cc, _stream()), "ub_softmax_ce")
+
+
+@_instrument("clip_zero_shot", 1)
+def clip_zero_shot(img_feat, text_feat, probs, T):
+    BT, D = img_feat.shape
+    Cc = text_feat.shape[0]
+    check(lib.ub_clip_zero_shot(_p(img_feat, F32, "img_feat"), _p(text_feat, F32, "text_feat"), _p(probs, F32, "probs"), BT // T, T, Cc, D,
+                                _stream()), "ub_clip_zero_shot")
+    return probs
+
+
+@_instrument("pseudo_label_fusion", 1)
+def pseudo_label_fusion(logits_full, clip_probs, threshold, conf_weighted, msp, pseudo, sel, weight):
+    B, Cc = logits_full.shape
+    check(lib.ub_pseudo_label_fusion(_p(logits_full, F32, "logits_full"), _p(clip_probs, F32, "clip_probs"), threshold, int(conf_weighted),
+                                     _p(msp, F32, "msp"), _p(pseudo, I32, "pseudo"), _p(sel, U8, "sel"), _p(weight, F32, "weight"), B, Cc,
+                                     _stream()), "ub_pseudo_label_fusion")
