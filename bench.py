@@ -184,7 +184,11 @@ def main():
     student, teacher = student.to(dev).train(), teacher.to(dev).eval()
     model = DataParallel(student)
     model.grad_sync = GradSync() if world > 1 else None
-    eng = Stage1Engine(student, teacher, mask_ratio=0.8, lr=1.5e-4 * B * world / 256, weight_decay=0.05, grad_sync=model.grad_sync)
+    use_graph = os.environ.get("UB_NO_GRAPH", "0") != "1"
+    eng = Stage1Engine(student, teacher, mask_ratio=0.8, lr=1.5e-4 * B * world / 256, weight_decay=0.05, grad_sync=model.grad_sync,
+                       use_graph=use_graph)
+    from unite_b200 import engine_for_pretraining as efp
+    efp._ENGINES[(id(student), id(teacher))] = eng          # train_one_epoch (e2e) drives the same engine / optimizer state
 
     # ---- device-resident inputs (value) ------------------------------------------------------------------------
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
@@ -226,6 +230,7 @@ def main():
 
     class _Args:
         log_freq = 1          # read the loss back every step: the D2H of the step's result is inside the timed region
+        use_cuda_graph = use_graph
     train_one_epoch(model, warm_loader, None, eng.optimizer, dev, 0, None, teacher_model=teacher, mask_type="attention",
                     mask_ratio=0.8, args=_Args)
     sync_all()
@@ -246,6 +251,7 @@ def main():
     roof, breakdown = None, None
     if rank == 0:
         ops.PROFILE = []
+    eng.use_graph = False              # the instrumented step runs eagerly (events around every launch)
     eng.step(*dev_batches[0])          # every rank runs it (the step contains the all-reduce); only rank 0 records
     sync_all()
     if rank == 0:
@@ -297,7 +303,7 @@ def main():
         ms_per_step=round(ms_per_step, 3), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
         config=dict(workload="BASELINE configs[1]: stage-1 UMT masked distillation, ViT-B/16 student (80% CLIP-attn mask, 320 of 1568 tokens) + "
                              "frozen CLIP ViT-B/16 teacher, 8x224^2, tubelet 1, K=6 aligned layers, AdamW",
-                    per_gpu_batch=B, global_batch=B * world, parallelism=f"dp{world}", l2_policy="inputs_exceed_l2 (154 MB clip batch + "
+                    per_gpu_batch=B, global_batch=B * world, parallelism=f"dp{world}", cuda_graph=use_graph, l2_policy="inputs_exceed_l2 (154 MB clip batch + "
                     "multi-GB activations per step vs 126 MB L2; two input batches alternate)", init="random (reference initialisers), seed 0"),
         clocks=clocks,
         e2e=dict(value=round(e2e_value, 2), unit="clips/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=round(e2e_ms, 3),

@@ -127,6 +127,10 @@ UB_API int ub_sumsq(const float* g, int64_t n, float* out /* accumulated */, voi
 UB_API int ub_adamw(float* p, const float* g, float* m, float* v, void* w_bf16 /* may be NULL */, int64_t n,
                     int64_t n_decay, float lr, float wd, float beta1, float beta2, float eps, int step, float grad_scale,
                     void* stream);
+/* same update, per-step scalars in device memory: hyper[8] = lr, wd, beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t), grad_scale
+ * (lets the launch sit in a CUDA graph replayed every step) */
+UB_API int ub_adamw_dev(float* p, const float* g, float* m, float* v, void* w_bf16 /* may be NULL */, int64_t n,
+                        int64_t n_decay, const float* hyper, void* stream);
 UB_API int ub_cast_bf16(const float* x, void* out, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -58,6 +58,38 @@ __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, cons
   }
 }
 
+// Same update with the per-step scalars read from DEVICE memory (hyper[8] = lr, wd, beta1, beta2, eps, bc1, sqrt(bc2),
+// grad_scale), so the launch can live inside a CUDA graph that is replayed every step while the host only refreshes
+// those 32 bytes.
+__global__ void __launch_bounds__(256) adamw_dev_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                                        float4* __restrict__ v, uint2* __restrict__ w_bf16, long n4, long n4_decay,
+                                                        const float* __restrict__ hyper) {
+  const float lr = hyper[0], wd = hyper[1], beta1 = hyper[2], beta2 = hyper[3], eps = hyper[4], bc1 = hyper[5], bc2_sqrt = hyper[6],
+              grad_scale = hyper[7];
+  const float step_size = lr / bc1;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    const float decay = (i < n4_decay) ? (1.0f - lr * wd) : 1.0f;
+#define UB_ADAM_ONE(c)                                               \
+  {                                                                  \
+    const float gr = gg.c * grad_scale;                              \
+    pp.c *= decay;                                                   \
+    mm.c = beta1 * mm.c + (1.0f - beta1) * gr;                       \
+    vv.c = beta2 * vv.c + (1.0f - beta2) * gr * gr;                  \
+    pp.c -= step_size * (mm.c / (sqrtf(vv.c) / bc2_sqrt + eps));     \
+  }
+    UB_ADAM_ONE(x) UB_ADAM_ONE(y) UB_ADAM_ONE(z) UB_ADAM_ONE(w)
+#undef UB_ADAM_ONE
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    if (w_bf16) {
+      uint2 o;
+      o.x = pack_bf16x2(pp.x, pp.y);
+      o.y = pack_bf16x2(pp.z, pp.w);
+      w_bf16[i] = o;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ out, long n4) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
     const float4 v = x[i];
@@ -96,6 +128,16 @@ extern "C" int ub_adamw(float* p, const float* g, float* m, float* v, void* w_bf
                                                                    (uint2*)w_bf16, n / 4, n_decay / 4, lr, wd, beta1, beta2, eps,
                                                                    bc1, sqrtf(bc2), grad_scale);
   return check_launch("adamw_kernel");
+}
+
+extern "C" int ub_adamw_dev(float* p, const float* g, float* m, float* v, void* w_bf16, int64_t n, int64_t n_decay,
+                            const float* hyper, void* stream) {
+  UB_REQUIRE(p && g && m && v && hyper, "adamw_dev: null pointer");
+  UB_REQUIRE(n > 0 && n % 4 == 0 && n_decay % 4 == 0 && n_decay >= 0 && n_decay <= n,
+             "adamw_dev: n=%lld and n_decay=%lld must be multiples of 4", (long long)n, (long long)n_decay);
+  adamw_dev_kernel<<<flat_grid4(n / 4), 256, 0, (cudaStream_t)stream>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v,
+                                                                       (uint2*)w_bf16, n / 4, n_decay / 4, hyper);
+  return check_launch("adamw_dev_kernel");
 }
 
 extern "C" int ub_cast_bf16(const float* x, void* out, int64_t n, void* stream) {

@@ -42,6 +42,27 @@ class FusedAdamW:
     def zero_grad(self, set_to_none: bool = False):
         self.arena.grads.zero_()
 
+    # ---- graph-friendly form: scalars live in device memory, refreshed by one 32-byte async copy per step ----------
+    def prepare_step(self, grad_scale: float = 1.0):
+        """Host side of a (possibly graph-replayed) step: advance the step counter and upload lr / wd / bias corrections."""
+        if not hasattr(self, "_hyper_dev"):
+            self._hyper_dev = torch.zeros(8, device=self.arena.device, dtype=F32)
+            self._hyper_pin = [torch.zeros(8, dtype=F32).pin_memory() for _ in range(4)]
+        self.step_count += 1
+        g0 = self.param_groups[0]
+        b1, b2 = self.betas
+        hp = self._hyper_pin[self.step_count % 4]
+        hp.copy_(torch.tensor([g0["lr"], g0["weight_decay"], b1, b2, self.eps, 1.0 - b1 ** self.step_count,
+                               math.sqrt(1.0 - b2 ** self.step_count), grad_scale], dtype=F32))
+        self._hyper_dev.copy_(hp, non_blocking=True)
+
+    def step_dev(self):
+        """Device side: grad-norm + AdamW reading the scalars uploaded by prepare_step (capturable in a CUDA graph)."""
+        a = self.arena
+        self.gnorm_sq.zero_()
+        ops.sumsq(a.grads, self.gnorm_sq)
+        ops.adamw_dev(a.params, a.grads, self.exp_avg, self.exp_avg_sq, a.w16, a.n_decay, self._hyper_dev)
+
     def step(self, grad_scale: float = 1.0):
         a = self.arena
         self.step_count += 1
@@ -66,8 +87,15 @@ class FusedAdamW:
 
 class Stage1Engine:
     def __init__(self, student: AdaptationVisionTransformer, teacher: ClipVisionTransformer, mask_ratio: float = 0.8,
-                 lr: float = 1.5e-4, weight_decay: float = 0.05, betas=(0.9, 0.95), eps: float = 1e-8, grad_sync=None):
+                 lr: float = 1.5e-4, weight_decay: float = 0.05, betas=(0.9, 0.95), eps: float = 1e-8, grad_sync=None,
+                 use_graph: bool = False):
+        """use_graph: after two eager steps of a given batch shape, the whole step (teacher, mask, student fwd/bwd,
+        gradient all-reduce, grad-norm, AdamW) is captured once in a CUDA graph and replayed — the ~460 launches of a step
+        then cost one launch.  Requires DropPath off (random draws inside a captured region would be frozen)."""
         self.student, self.teacher, self.mask_ratio = student, teacher, mask_ratio
+        self.use_graph = use_graph
+        self._graphs = {}
+        self._eager_steps = {}
         self.core = student.core()
         self.core.sync_shadow(force=True)
         self.optimizer = FusedAdamW(self.core.arena, lr, weight_decay, betas, eps)
@@ -109,11 +137,47 @@ class Stage1Engine:
         self.last = dict(attn=attn, mask=mask.view(B, Tp * P).bool(), vis_idx=vis_idx[0], targets=targets, outputs=x_clip)
         return self.loss
 
-    def step(self, videos, q, dp=None):
+    def _step_body_dev(self, videos, q):
         self.optimizer.zero_grad()
-        loss = self.forward_backward(videos, q, dp)
-        scale = 1.0
+        self.forward_backward(videos, q, None)
         if self.grad_sync is not None:
-            scale = self.grad_sync.all_reduce(self.core.arena.grads)
-        self.optimizer.step(grad_scale=scale)
-        return loss
+            self.grad_sync.all_reduce(self.core.arena.grads)
+        self.optimizer.step_dev()
+
+    def step(self, videos, q, dp=None):
+        graphable = self.use_graph and dp is None and not (self.student.training and any(r > 0 for r in self.student.encoder.drop_path_rates))
+        if not graphable:
+            self.optimizer.zero_grad()
+            loss = self.forward_backward(videos, q, dp)
+            scale = 1.0
+            if self.grad_sync is not None:
+                scale = self.grad_sync.all_reduce(self.core.arena.grads)
+            self.optimizer.step(grad_scale=scale)
+            return loss
+        key = (tuple(videos.shape), tuple(q.shape))
+        scale = 1.0 / self.grad_sync.world if self.grad_sync is not None else 1.0
+        self.optimizer.prepare_step(grad_scale=scale)
+        if key not in self._graphs:
+            n = self._eager_steps.get(key, 0)
+            if n < 2:                                   # warm-up: lazy attribute setting, workspace allocation, NCCL init
+                self._eager_steps[key] = n + 1
+                self._step_body_dev(videos, q)
+                return self.loss
+            sv, sq = torch.empty_like(videos), torch.empty_like(q)
+            sv.copy_(videos); sq.copy_(q)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.LAUNCHES
+            with torch.cuda.graph(g):
+                self._step_body_dev(sv, sq)
+            n_kernels = ops.LAUNCHES - n0               # kernels of ours recorded in the graph (capture executes nothing)
+            ops.LAUNCHES = n0
+            self._graphs[key] = (g, sv, sq, n_kernels)
+        g, sv, sq, n_kernels = self._graphs[key]
+        ops.LAUNCHES += n_kernels                       # every replay launches all of them
+        if videos.data_ptr() != sv.data_ptr():
+            sv.copy_(videos, non_blocking=True)
+        if q.data_ptr() != sq.data_ptr():
+            sq.copy_(q, non_blocking=True)
+        g.replay()
+        return self.loss

@@ -17,7 +17,7 @@ from .engine import Stage1Engine
 _ENGINES = {}
 
 
-def _engine_for(model, teacher_model, mask_ratio, optimizer):
+def _engine_for(model, teacher_model, mask_ratio, optimizer, use_graph=False):
     student = model.module if hasattr(model, "module") else model
     teacher = teacher_model.module if hasattr(teacher_model, "module") else teacher_model
     key = (id(student), id(teacher))
@@ -25,7 +25,7 @@ def _engine_for(model, teacher_model, mask_ratio, optimizer):
         gs = getattr(model, "grad_sync", None)
         if gs is not None:
             gs.arena = student.core().arena
-        _ENGINES[key] = Stage1Engine(student, teacher, mask_ratio=mask_ratio, grad_sync=gs)
+        _ENGINES[key] = Stage1Engine(student, teacher, mask_ratio=mask_ratio, grad_sync=gs, use_graph=use_graph)
         if optimizer is not None and hasattr(optimizer, "arena"):
             _ENGINES[key].optimizer = optimizer
     return _ENGINES[key]
@@ -42,7 +42,7 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
     if max_norm:
         raise NotImplementedError("clip_grad is null in every shipped config")
     model.train()
-    eng = _engine_for(model, teacher_model, mask_ratio, optimizer)
+    eng = _engine_for(model, teacher_model, mask_ratio, optimizer, use_graph=bool(getattr(args, "use_cuda_graph", False)))
     opt = eng.optimizer
     dev = eng.core.arena.device
     log_freq = getattr(args, "log_freq", 10) if args is not None else 10
@@ -51,14 +51,16 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
     n = 0
     it_target = iter(data_loader_train_target) if data_loader_train_target is not None else None
     last_loss = float("nan")
-    for step, batch in enumerate(data_loader):
-        it = start_steps + step
-        for group in opt.param_groups:                                         # run_stage1.py:326-338
-            if lr_schedule_values is not None:
-                group["lr"] = lr_schedule_values[min(it, len(lr_schedule_values) - 1)] * group.get("lr_scale", 1.0)
-            if wd_schedule_values is not None and group["weight_decay"] > 0:
-                group["weight_decay"] = wd_schedule_values[min(it, len(wd_schedule_values) - 1)]
+    # Input pipeline: the H2D copy of batch i+1 runs on a side stream while batch i computes (pinned host memory, as
+    # DataLoader(pin_memory=True) + .to(device, non_blocking=True) at run_stage1.py:349 intend), and the per-step loss is
+    # read back through a pinned buffer one step late, so neither direction stalls the launch queue.
+    copy_stream = torch.cuda.Stream(device=dev)
+    pin_loss = [torch.empty(1, pin_memory=True) for _ in range(2)]
+    loss_ev = [None, None]
+
+    def fetch(batch):
         videos, noise = batch[0], (batch[3] if len(batch) > 3 else None)
+        nonlocal it_target
         if it_target is not None:                                              # run_stage1.py:343-347
             try:
                 tb = next(it_target)
@@ -68,23 +70,59 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
             videos = torch.cat([videos, tb[0]], dim=0)
             if noise is not None and len(tb) > 3:
                 noise = torch.cat([noise, tb[3]], dim=0)
-        videos = videos.to(dev, non_blocking=True)                             # run_stage1.py:349
+        with torch.cuda.stream(copy_stream):
+            v = videos.to(dev, non_blocking=True)                              # run_stage1.py:349
+            q = None if noise is None else noise.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return v, q, ev
+
+    def check(slot):
+        nonlocal last_loss
+        if loss_ev[slot] is not None:
+            loss_ev[slot].synchronize()
+            last_loss = float(pin_loss[slot][0])
+            loss_ev[slot] = None
+            if not math.isfinite(last_loss):
+                print("Loss is {}, stopping training".format(last_loss))
+                sys.exit(1)
+
+    it_loader = iter(data_loader)
+    nxt = next(it_loader, None)
+    staged = fetch(nxt) if nxt is not None else None
+    step = 0
+    while staged is not None:
+        videos, noise, ev = staged
+        nxt = next(it_loader, None)
+        it = start_steps + step
+        for group in opt.param_groups:                                         # run_stage1.py:326-338
+            if lr_schedule_values is not None:
+                group["lr"] = lr_schedule_values[min(it, len(lr_schedule_values) - 1)] * group.get("lr_scale", 1.0)
+            if wd_schedule_values is not None and group["weight_decay"] > 0:
+                group["weight_decay"] = wd_schedule_values[min(it, len(wd_schedule_values) - 1)]
+        torch.cuda.current_stream(dev).wait_event(ev)
+        videos.record_stream(torch.cuda.current_stream(dev))
         if noise is None:
             frames = videos.shape[0] * (videos.shape[2] // eng.teacher.kernel_size)
             noise = torch.empty(frames, (videos.shape[3] // 16) * (videos.shape[4] // 16), device=dev).exponential_(1)
         else:
-            noise = noise.to(dev, non_blocking=True)
+            noise.record_stream(torch.cuda.current_stream(dev))
+        staged = fetch(nxt) if nxt is not None else None                       # overlaps with this step's compute
         loss = eng.step(videos, noise)
         loss_sum += loss
         gn_sum += opt.grad_norm(1.0 / (eng.grad_sync.world if eng.grad_sync is not None else 1))
         n += 1
         if log_freq and (step + 1) % log_freq == 0:
-            last_loss = loss.item()                                            # the only host read inside the loop
-            if not math.isfinite(last_loss):
-                print("Loss is {}, stopping training".format(last_loss))
-                sys.exit(1)
+            slot = (step // log_freq) & 1
+            check(slot)                                                        # the read issued two log points ago
+            pin_loss[slot].copy_(loss, non_blocking=True)                      # D2H of this step's loss (async)
+            loss_ev[slot] = torch.cuda.Event()
+            loss_ev[slot].record()
         if lr_scheduler is not None:
             lr_scheduler.step_update(start_steps + step)
+        step += 1
+    check(0)
+    check(1)
     stats = torch.cat([loss_sum, gn_sum]) / max(n, 1)
     if torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
         torch.distributed.all_reduce(stats)                                    # utils.py:239-241 (epoch-end meter sync)
