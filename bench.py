@@ -289,9 +289,18 @@ def main():
             json.dump(dict(ms_per_step_sum_of_ops=total_ms, ops=breakdown, gemm_tflops=achieved,
                            gemm_shapes_M_N_K_aT_bT_fp32out=gs), open(args.profile_out, "w"), indent=1)
 
-    if rank != 0:
+    def finish():
+        # NCCL communicators referenced by captured CUDA graphs can hang in destroy_process_group(): leave together, hard
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -314,8 +323,7 @@ def main():
                  of_measured_sustained=round(per_gpu * F_ALG_GFLOP_PER_CLIP / 1e3 / measured_peaks()["bf16"], 4)),
         loss=round(loss_value, 5), e2e_loss=round(stats["loss"], 5), op_breakdown_ms=breakdown)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
