@@ -145,3 +145,24 @@ def test_optimizer_step_matches_torch_adamw():
     for k, p in ps.items():
         assert rel_l2(student.state_dict()[k], p) < 1e-6, k
     assert abs(eng.optimizer.grad_norm().item() - torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).item()) < 1e-3
+
+
+def test_vitl_student_tubelet2_teacher_kernel2_against_oracle():
+    """BASELINE configs[4] shapes: ViT-L/16 student (D=1024, 24 layers, 16 heads), 16 frames, tubelet 2, CLIP-B/16 teacher built
+    with kernel_size=2 -> 1568 tokens, 320 visible.  B=1, against the oracle on the CPU."""
+    from oracle import unite_oracle as O
+    from oracle.weights import seeded_state
+    from unite_b200.engine import Stage1Engine
+    scfg = O.StudentCfg(embed_dim=1024, depth=24, num_heads=16, num_frames=16, tubelet_size=2)
+    tcfg = O.TeacherCfg(kernel_size=2)
+    student, teacher = build_student(scfg), build_teacher(tcfg)
+    ssd = seeded_state({k: tuple(v.shape) for k, v in student.state_dict().items()}, 5)
+    tsd = seeded_state({k: tuple(v.shape) for k, v in teacher.state_dict().items()}, 6)
+    student.load_state_dict(ssd); teacher.load_state_dict(tsd)
+    g = torch.Generator().manual_seed(77)
+    videos = torch.randn(1, 3, 16, 224, 224, generator=g)
+    q = torch.empty(8, 196).exponential_(1, generator=g)
+    ref = O.stage1_step(ssd, tsd, videos, q, scfg, tcfg, mask_ratio=0.8)
+    assert ref["vis_idx"].shape == (1, 320)
+    eng = Stage1Engine(student.cuda().train(), teacher.cuda().eval(), mask_ratio=0.8)
+    _check_step(eng, ref, videos, q, big_grad_only=True)

@@ -113,9 +113,14 @@ class VisionTransformer(nn.Module):
 
     # ---- compute ---------------------------------------------------------------------------
     @torch.no_grad()
-    def forward_features(self, x, patches=None):
+    def forward_features(self, x, patches=None, select=None):
         """Runs the tower.  Returns (layers: list of K fp32 [B*T'*(HW+1), W] residual-stream snapshots after the
-        blocks in clip_return_layers, attn fp32 [B*T', HW] or None, patches bf16 im2col rows)."""
+        blocks in clip_return_layers, attn fp32 [B*T', HW] or None, patches bf16 im2col rows).
+
+        select: optional callable(attn) -> int32 row indices (into the [frames*(HW+1)] token stream) of the tokens whose
+        features will be used.  The LAST block's attention map only needs its QKV projection, and nothing after it reads
+        the other tokens, so when the last block is a returned layer its out_proj / MLP run on the selected rows only
+        (80 % fewer rows in stage 1); that snapshot is then [n_selected, W] and `self.last_gathered` is True."""
         w = self._weights()
         B, _, T, H, Wd = x.shape
         ks, W = self.kernel_size, self.width
@@ -137,6 +142,7 @@ class VisionTransformer(nn.Module):
         ret = self.transformer.return_index
         nblk = len(self.transformer.resblocks)
         scale = 64 ** -0.5
+        self.last_gathered = False
         for i, blk in enumerate(self.transformer.resblocks):
             ops.layernorm_fwd(cur, blk.ln_1.weight.detach(), blk.ln_1.bias.detach(), blk.ln_1.eps, bufs["h"])
             ops.gemm(bufs["h"], w[f"{i}.in_proj"], bufs["qkv"], bias=blk.attn.in_proj_bias.detach())
@@ -144,6 +150,20 @@ class VisionTransformer(nn.Module):
                 attn = torch.empty(frames, P, device=x.device, dtype=F32)
                 ops.cls_attn(bufs["qkv"], attn, frames, S, self.heads, scale)
             ops.attn_fwd(bufs["qkv"], bufs["o"], None, frames, S, self.heads, scale)
+            if i == nblk - 1 and select is not None and attn is not None and i in ret:
+                rows = select(attn)
+                n = rows.numel()
+                tb = self._tail_buffers(n)
+                ops.gather_rows(bufs["o"], rows, tb["o"])
+                ops.gather_rows(cur, rows, tb["x"])
+                ops.gemm(tb["o"], w[f"{i}.out_proj"], tb["mid"], bias=blk.attn.out_proj.bias.detach(), residual=tb["x"])
+                ops.layernorm_fwd(tb["mid"], blk.ln_2.weight.detach(), blk.ln_2.bias.detach(), blk.ln_2.eps, tb["h"])
+                ops.gemm(tb["h"], w[f"{i}.c_fc"], tb["u"], bias=blk.mlp.c_fc.bias.detach(), act=ops.UB_ACT_QUICKGELU)
+                ops.gemm(tb["u"], w[f"{i}.c_proj"], tb["out"], bias=blk.mlp.c_proj.bias.detach(), residual=tb["mid"])
+                keep.append(tb["out"])
+                self.last_gathered = True
+                self.last_stream = None
+                return keep, attn, patches
             ops.gemm(bufs["o"], w[f"{i}.out_proj"], mid, bias=blk.attn.out_proj.bias.detach(), residual=cur)
             ops.layernorm_fwd(mid, blk.ln_2.weight.detach(), blk.ln_2.bias.detach(), blk.ln_2.eps, bufs["h"])
             ops.gemm(bufs["h"], w[f"{i}.c_fc"], bufs["u"], bias=blk.mlp.c_fc.bias.detach(), act=ops.UB_ACT_QUICKGELU)
@@ -156,17 +176,28 @@ class VisionTransformer(nn.Module):
         self.last_stream = cur        # residual stream after the final block (CLS rows feed the stage-3 zero-shot head)
         return keep, attn, patches
 
+    def _tail_buffers(self, n):
+        key = ("tail", n)
+        if key not in self._bufs:
+            dev, W = self.proj.device, self.width
+            self._bufs[key] = dict(o=torch.empty(n, W, device=dev, dtype=BF16), x=torch.empty(n, W, device=dev, dtype=F32),
+                                   mid=torch.empty(n, W, device=dev, dtype=F32), h=torch.empty(n, W, device=dev, dtype=BF16),
+                                   u=torch.empty(n, 4 * W, device=dev, dtype=BF16), out=torch.empty(n, W, device=dev, dtype=F32))
+        return self._bufs[key]
+
     @torch.no_grad()
     def project_rows(self, layers: List[torch.Tensor], rows: torch.Tensor) -> torch.Tensor:
         """ln_post -> @proj -> L2-normalise (clip.py:168-173) on the given residual-stream rows only.
-        rows int32 [n] (row index into each layer snapshot).  Returns fp32 [K, n, output_dim]."""
+        rows int32 [n] (row index into each layer snapshot; a snapshot that already holds exactly those n rows — the
+        truncated last block of forward_features(select=...) — is used as is).  Returns fp32 [K, n, output_dim]."""
         w = self._weights()
         K, n = len(layers), rows.numel()
         dev = rows.device
         z = torch.empty(K * n, self.width, device=dev, dtype=BF16)
         for k, xk in enumerate(layers):
+            gathered = getattr(self, "last_gathered", False) and k == K - 1 and xk.shape[0] == n
             ops.layernorm_fwd(xk, self.ln_post.weight.detach(), self.ln_post.bias.detach(), self.ln_post.eps, z[k * n:(k + 1) * n],
-                              src_rows=rows)
+                              src_rows=None if gathered else rows)
         out = torch.empty(K * n, self.output_dim, device=dev, dtype=F32)
         ops.gemm(z, w["proj_t"], out)
         ops.l2norm_rows(out)

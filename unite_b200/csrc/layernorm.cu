@@ -205,7 +205,7 @@ UB_DEVINL void block_col_reduce_atomic(const RowT<NV>& part, float* s_buf, float
 }
 
 template <int NV>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const LnBwdArgs a) {
   extern __shared__ float s_red[];  // [warps][D]
   const int lane = threadIdx.x & 31;
   constexpr int nv = NV;

@@ -119,14 +119,26 @@ class Stage1Engine:
             n_tok = B * (videos.shape[2] // ks) * (videos.shape[3] // 16) * (videos.shape[4] // 16)
             patches = torch.empty(n_tok, 3 * ks * 256, device=videos.device, dtype=BF16)
             ops.patchify(videos, patches, ks)
-        layers, attn, _ = teacher.forward_features(videos, patches)
+        sel = {}
+
+        def select(attn):
+            # run_stage1.py:379-387 on the device, called by the teacher as soon as its last block's attention map exists
+            frames, P = attn.shape
+            Tp = frames // B
+            n_vis = self.n_visible(P)
+            sel["mask"] = torch.empty(1, frames * P, device=videos.device, dtype=U8)
+            sel["vis_idx"] = torch.empty(1, B, Tp * n_vis, device=videos.device, dtype=I32)
+            sel["tea_rows"] = torch.empty(1, B, Tp * n_vis, device=videos.device, dtype=I32)
+            ops.mask_select(attn if attn_override is None else attn_override, q, sel["mask"], sel["vis_idx"], sel["tea_rows"], Tp, 1,
+                            n_vis)
+            return sel["tea_rows"].view(-1)
+
+        layers, attn, _ = teacher.forward_features(videos, patches, select=select)
+        if not sel:                                                               # teacher without return_attn / last-layer tap
+            select(attn)
         frames, P = attn.shape
         Tp = frames // B
-        n_vis = self.n_visible(P)
-        mask = torch.empty(1, frames * P, device=videos.device, dtype=U8)
-        vis_idx = torch.empty(1, B, Tp * n_vis, device=videos.device, dtype=I32)
-        tea_rows = torch.empty(1, B, Tp * n_vis, device=videos.device, dtype=I32)
-        ops.mask_select(attn if attn_override is None else attn_override, q, mask, vis_idx, tea_rows, Tp, 1, n_vis)
+        mask, vis_idx, tea_rows = sel["mask"], sel["vis_idx"], sel["tea_rows"]
         targets = teacher.project_rows(layers, tea_rows.view(-1))                 # [K, B*Nv, C]
         if dp is None and self.student.training:
             dp = drop_path_factors(self.student.encoder.drop_path_rates, B, videos.device)

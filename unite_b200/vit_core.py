@@ -95,6 +95,10 @@ class ViTTrunk:
         o, k = self.arena.offsets[f"{self.prefix}blocks.{l}.attn.q_bias"]
         return self.arena.params[o:o + 3 * k]
 
+    def qkv_bias_grad(self, l):
+        o, k = self.arena.offsets[f"{self.prefix}blocks.{l}.attn.q_bias"]
+        return self.arena.grads[o:o + 3 * k]
+
     def workspace(self, B, N, save) -> TrunkWorkspace:
         """Workspaces holding saved activations stay `busy` until their backward ran, so a second graph-attached
         forward of the same shape (stage 3 runs several before one backward) gets its own buffers."""
@@ -185,8 +189,11 @@ class ViTTrunk:
             ops.attn_bwd(L.qkv, L.o, ws.d_o, L.lse, ws.d_ws, ws.dqkv, ws.B, N, self.H, self.scale)
             ops.gemm(ws.dqkv, self.w(b + "attn.qkv.weight"), ws.d_h, b_t=True)
             self._wgrad(ws.dqkv, L.h1, self.g(b + "attn.qkv.weight"))
-            ops.colsum_bf16(ws.dqkv[:, :D], self.g(b + "attn.q_bias"))
-            ops.colsum_bf16(ws.dqkv[:, 2 * D:], self.g(b + "attn.v_bias"))
+            # q_bias | (always-zero k gap) | v_bias are one contiguous 3D span of the gradient arena: one column-sum pass
+            # over all of dqkv, then clear the gap (the key bias is structurally zero, modeling_finetune.py:104)
+            gq = self.qkv_bias_grad(l)
+            ops.colsum_bf16(ws.dqkv, gq)
+            gq[D:2 * D].zero_()
             # next consumer of dxs: block l-1's MLP branch (unless a tap re-emits it) or the patch embedding
             emit = (l - 1) not in tap_grads
             s_next = None if (dp is None or l == 0) else dp[l - 1, 1]
