@@ -277,9 +277,21 @@ def main():
                 n_gemm += 1
         total_ms = sum(v[1] for v in by.values())
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        top = None
+        tp = os.path.join(ROOT, "profiles", "gemm_ncu_r01c.json")
+        if os.path.exists(tp):
+            t = json.load(open(tp))
+            key = str((t["shape_M_N_K"][0], t["shape_M_N_K"][1], t["shape_M_N_K"][2], False, False, False))
+            if key in shapes:
+                us = shapes[key][1] / shapes[key][0] * 1e3
+                top = dict(shape_M_N_K=t["shape_M_N_K"], launches_per_step=shapes[key][0], avg_launch_us=round(us, 1),
+                           achieved=round(t["algorithmic_flops"] / (us * 1e-6) / 1e12, 1), unit="TFLOP/s",
+                           frac=round(t["algorithmic_flops"] / (us * 1e-6) / 1e12 / peaks["bf16"], 4),
+                           traffic=t["dram_bytes_read"] + t["dram_bytes_write"], algorithmic_bytes=t["algorithmic_bytes"],
+                           traffic_source=t["source"])
         roof = dict(bound="tensor", kernel="ub::gemm_kernel (tcgen05/TMEM/TMA bf16 GEMM family, all launches of one step)",
                     achieved=round(achieved, 1), peak=peaks["bf16"], unit="TFLOP/s", frac=round(achieved / peaks["bf16"], 4),
-                    traffic=None, peak_source=peaks["source"], launches_per_step=n_gemm,
+                    traffic=None, top_shape=top, peak_source=peaks["source"], launches_per_step=n_gemm,
                     alg_flops_per_launch=gemm_flops / n_gemm, avg_launch_us=round(gemm_ms / n_gemm * 1e3, 2),
                     share_of_step=round(gemm_ms / total_ms, 4))
         breakdown = {k: dict(launches=v[0], ms=round(v[1], 3)) for k, v in sorted(by.items(), key=lambda kv: -kv[1][1])}
