@@ -1,0 +1,13 @@
+#!/bin/bash
+# usage (under gpurun): tools/attn_bwd_sweep.sh  -> gpurun_out/attn_bwd_sweep.log ; each shape in its own process + timeout
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+L=gpurun_out/attn_bwd_sweep.log
+: > $L
+for shp in "2 17 2" "3 128 4" "2 160 3" "4 197 12" "2 256 3" "3 288 5" "2 300 3" "3 320 12" "32 320 12 time" "32 320 16 time"; do
+  echo "=== $shp" >> $L
+  timeout 90 python tools/attn_bwd_check.py $shp >> $L 2>&1
+  echo "rc=$?" >> $L
+done
+UB_ATTN_BWD_TC=0 timeout 90 python tools/attn_bwd_check.py 32 320 12 time >> $L 2>&1
+tail -120 $L

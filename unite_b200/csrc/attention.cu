@@ -542,6 +542,8 @@ __global__ void cls_attn_kernel(const bf16* __restrict__ qkv, float* __restrict_
 
 namespace ub {
 int launch_attn_fwd_tc(const void* qkv, void* o, int n_seq, int S, int H, float scale, cudaStream_t stream);
+int launch_attn_bwd_tc(const void* qkv, const void* d_o, const float* lse, const float* Dv, void* dqkv, int n_seq, int S, int H,
+                       float scale, cudaStream_t stream);
 }
 using namespace ub;
 
@@ -570,6 +572,13 @@ extern "C" int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, cons
   const int n_rows = n_seq * S;
   attn_bwd_prep_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>((const bf16*)o, (const bf16*)d_o, D_ws, n_rows, S, H);
   if (check_launch("attn_bwd_prep_kernel")) return 1;
+  // short sequences (the student's <= 320 visible tokens): single-pass tcgen05 / TMEM kernel
+  static int use_tc = -1;
+  if (use_tc < 0) {
+    const char* e = getenv("UB_ATTN_BWD_TC");
+    use_tc = e ? atoi(e) : 1;
+  }
+  if (use_tc && S <= 320) return launch_attn_bwd_tc(qkv, d_o, lse, D_ws, dqkv, n_seq, S, H, scale, st);
   dim3 grid((S + TQ - 1) / TQ, H, n_seq);
   constexpr int SMEM_DKV = 6 * TQ * 128 + 4 * TQ * 4;
   constexpr int SMEM_DQ = 6 * TQ * 128;
