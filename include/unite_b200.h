@@ -64,6 +64,9 @@ UB_API int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* 
  * ub_attn_bwd is their autograd backward (D_ws: fp32 [n_seq,H,S] scratch); ub_cls_attn is clip.py:95-96,183:
  * out[n_seq, S-1] = head-averaged softmax row of the CLS query (token 0) over the patch keys.
  * ---------------------------------------------------------------------------------------------- */
+/* diagnostic: how many 4-CTA clusters of the GEMM kernel the device can hold at once (0 = cluster-of-4 tiles are not used) */
+UB_API int ub_gemm_cluster4_capacity(void);
+
 UB_API int ub_attn_fwd(const void* qkv, void* o, float* lse /* may be NULL */, int n_seq, int S, int H, float scale,
                        void* stream);
 UB_API int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* D_ws, void* dqkv,

@@ -60,7 +60,7 @@ def run(M, N, K, a_mn=0, b_mn=0, out_fp32=0, bias=False, act=0, resid=False, spl
 
 
 if __name__ == "__main__":
-    print(torch.cuda.get_device_name(0), "SMs", cabi.lib.ub_sm_count())
+    print(torch.cuda.get_device_name(0), "SMs", cabi.lib.ub_sm_count(), "cluster-of-4 capacity", cabi.lib.ub_gemm_cluster4_capacity())
     if len(sys.argv) > 1 and sys.argv[1] == "one":
         M, N, K = map(int, sys.argv[2:5])
         kw = dict(a.split("=") for a in sys.argv[5:])

@@ -17,8 +17,9 @@
 //   warp 2        loads LSE * log2e and D = rowsum(dO o O) of the item into smem (double-buffered)
 //   warps 4-7     warpgroup 0: even 32-query chunks; dV epilogue; dQ tiles 0, 2
 //   warps 8-11    warpgroup 1: odd chunks; dK epilogue; dQ tile 1
-// TMEM columns: [0,32) S^T wg0 | [32,64) dP^T wg0 | [64,96) S^T wg1 | [96,128) dP^T wg1 | [128,192) dV | [192,256) dK |
-//               [256,448) dQ, three 128-query tiles.  P^T / dS^T overwrite the first 16 columns of S^T / dP^T in place.
+// TMEM columns: three rotating chunk sets {S^T [0,32) | dP^T [32,64)} at 0, 64, 128 (chunk n uses set n % 3, so the S/dP
+//               MMAs run three chunks ahead of the warpgroups) | [192,256) dV | [256,320) dK | [320,512) dQ, three 128-query
+//               tiles.  P^T / dS^T overwrite the first 16 columns of S^T / dP^T in place.
 #include "common.cuh"
 #include <cstdlib>
 #include "../../include/unite_b200.h"
@@ -59,15 +60,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* qdo_empty = bars + 3;     // every MMA of the item has read Q / dO
   uint64_t* kv_full = bars + 4;       // [2]
   uint64_t* kv_empty = bars + 6;      // [2] every MMA of the key tile has read the slot
-  uint64_t* s_full = bars + 8;        // [2] S^T / dP^T of this warpgroup's chunk are in TMEM
-  uint64_t* p_ready = bars + 10;      // [2] P^T / dS^T written (TMEM + smem staging)
-  uint64_t* stage_free = bars + 12;   // the dQ MMAs that read the dS^T staging have completed
-  uint64_t* dkv_full = bars + 13;     // dV / dK of the key tile are final
-  uint64_t* dkv_free = bars + 14;     // ... and have been read out
-  uint64_t* dq_full = bars + 15;
-  uint64_t* dq_free = bars + 16;
-  uint64_t* ld_full = bars + 17;      // [2]
-  uint64_t* ld_empty = bars + 19;     // [2]
+  uint64_t* s_full = bars + 8;        // [3] S^T / dP^T of the chunk in TMEM set (n % 3) are complete
+  uint64_t* p_ready = bars + 11;      // [3] P^T / dS^T of that set written (TMEM + smem staging)
+  uint64_t* stage_free = bars + 14;   // the dQ MMAs that read the dS^T staging have completed
+  uint64_t* dkv_full = bars + 15;     // dV / dK of the key tile are final
+  uint64_t* dkv_free = bars + 16;     // ... and have been read out
+  uint64_t* dq_full = bars + 17;
+  uint64_t* dq_free = bars + 18;
+  uint64_t* ld_full = bars + 19;      // [2]
+  uint64_t* ld_empty = bars + 21;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + ABT_NBAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,10 +83,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 4);
       mbar_init(&ld_full[i], 1);
       mbar_init(&ld_empty[i], 8);
+    }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 4);
     }
     mbar_init(stage_free, 1);
     mbar_init(dkv_full, 1);
@@ -104,7 +107,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const int n_items = p.n_seq * p.H;
   const int nkt = p.nkt, nc = p.nc, total = p.nkt * p.nc;
-  constexpr uint32_t TM_DV = 128, TM_DK = 192, TM_DQ = 256;
+  constexpr uint32_t TM_DV = 192, TM_DK = 256, TM_DQ = 320;
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------ TMA producer
@@ -148,43 +151,43 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t aQ = (smem_u32(smem + ABT_Q) & 0x3FFFFu) >> 4, aDO = (smem_u32(smem + ABT_DO) & 0x3FFFFu) >> 4;
     const uint32_t aKV = (smem_u32(smem + ABT_KV) & 0x3FFFFu) >> 4, aDS = (smem_u32(smem + ABT_DS) & 0x3FFFFu) >> 4;
-    uint32_t n = 0, kvn = 0;              // chunks / key tiles consumed so far (all items of this CTA)
-    uint32_t la_n = 0, la_kvn = 0;        // look-ahead cursor: next S^T / dP^T chunk to issue
+    uint32_t kvn = 0, set = 0, ph = 0;    // key tiles consumed so far; TMEM set (n % 3) and phase ((n / 3) & 1) of chunk n
+    uint32_t la_kvn = 0, la_set = 0;      // look-ahead cursor: next S^T / dP^T chunk to issue (3 chunks ahead)
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       int la_kt = 0, la_c = 0;
       auto issue_sdp = [&]() {
-        const uint32_t g = la_n & 1u, slot = la_kvn & 1u;
+        const uint32_t slot = la_kvn & 1u;
         if (la_c == 0) mbar_wait(&kv_full[slot], (la_kvn >> 1) & 1u);
         if (la_kt == 0 && (la_c & 3) == 0) mbar_wait(&q_full[la_c >> 2], it & 1);
         tc_fence_after();
         const uint32_t kd = aKV + slot * 2048u + LO_K, vd = kd + 1024u;
         const uint32_t qd = aQ + (uint32_t)la_c * 256u + LO_K, dod = aDO + (uint32_t)la_c * 256u + LO_K;
-        const uint32_t dS = tb + g * 64u;
+        const uint32_t dS = tb + la_set * 64u;
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_ss_lo(dS, kd + k * 2, HI_K, qd + k * 2, HI_K, IDESC_S, k > 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_ss_lo(dS + 32, vd + k * 2, HI_K, dod + k * 2, HI_K, IDESC_S, k > 0);
-          umma_commit(&s_full[g]);
+          umma_commit(&s_full[la_set]);
         }
         __syncwarp();
-        ++la_n;
+        if (++la_set == 3) la_set = 0;
         if (++la_c == nc) { la_c = 0; ++la_kt; ++la_kvn; }
       };
       issue_sdp();
       if (total > 1) issue_sdp();
+      if (total > 2) issue_sdp();
       for (int kt = 0; kt < nkt; ++kt, ++kvn) {
         const uint32_t slot = kvn & 1u;
-        for (int c = 0; c < nc; ++c, ++n) {
-          const uint32_t g = n & 1u;
-          mbar_wait(&p_ready[g], (n >> 1) & 1u);
+        for (int c = 0; c < nc; ++c) {
+          mbar_wait(&p_ready[set], ph);
           if (c == 0) mbar_wait(dkv_free, (kvn & 1u) ^ 1u);
           const bool tile_end = (c & 3) == 3 || c == nc - 1;
           if (tile_end && kt == 0 && c < 4) mbar_wait(dq_free, (it & 1) ^ 1);
           tc_fence_after();
           const uint32_t dod = aDO + (uint32_t)c * 256u + LO_MN8, qd = aQ + (uint32_t)c * 256u + LO_MN8;
-          const uint32_t tP = tb + g * 64u;
+          const uint32_t tP = tb + set * 64u;
           const bool first = c == 0;
           if (elect_one()) {
             umma_ts_lo(tb + TM_DV, tP, dod, HI_K, IDESC_KV, !first);
@@ -209,6 +212,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
           }
           __syncwarp();
+          if (++set == 3) { set = 0; ph ^= 1u; }
           if (la_kt < nkt) issue_sdp();
         }
       }
@@ -235,7 +239,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int g = (warp - 4) >> 2;         // warpgroup
     const int sp = warp & 3;               // TMEM sub-partition = 32-row group of the key tile
     const uint32_t t_lane = tmem_base + ((uint32_t)(sp * 32) << 16);
-    const uint32_t t_s = t_lane + g * 64, t_dp = t_s + 32;
     const int krow = sp * 32 + lane;       // key row of this thread within the tile
     const uint32_t ds_row = smem_u32(smem + ABT_DS) + (uint32_t)krow * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
@@ -244,6 +247,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float sl2 = p.sl2;
     int it = 0;
     uint32_t m_seq = 0;                    // dS^T staging use counter (same sequence as the MMA issuer's)
+    uint32_t set = 0, ph = 0, par = 0;     // TMEM set (n % 3), its phase ((n / 3) & 1) and owner warpgroup (n & 1) of chunk n
+    uint32_t kvn = 0;
     // TMEM (32 rows x 64 fp32 columns at t_src) -> * mul -> bf16 -> swizzled slab -> TMA store at (col, row, seq)
     auto store_tile = [&](uint32_t t_src, float mul, int col, int row, int seq) {
       if (lane == 0) tma_store_wait_read<0>();
@@ -277,12 +282,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float* sL = reinterpret_cast<const float*>(smem + ABT_LD) + (it & 1) * 640;
       const float* sD = sL + 320;
       mbar_wait(&ld_full[it & 1], (it >> 1) & 1);
-      for (int idx = 0; idx < total; ++idx) {
-        const int kt = idx / nc, c = idx % nc;
-        const int n = it * total + idx;
-        if ((n & 1) == g) {
+      for (int kt = 0; kt < nkt; ++kt, ++kvn) {
+      for (int c = 0; c < nc; ++c) {
+        if (par == (uint32_t)g) {
           const bool key_ok = kt * 128 + krow < p.S;
-          mbar_wait(&s_full[g], (n >> 1) & 1);
+          const uint32_t t_s = t_lane + set * 64u, t_dp = t_s + 32u;
+          mbar_wait(&s_full[set], ph);
           tc_fence_after();
           uint32_t sv[32], dv[32];
           tmem_ld_32x32(t_s, sv);
@@ -329,12 +334,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           tc_fence_before();
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&p_ready[g]);
+          if (lane == 0) mbar_arrive(&p_ready[set]);
         }
+        par ^= 1u;
+        if (++set == 3) { set = 0; ph ^= 1u; }
         if ((c & 3) == 3 || c == nc - 1) ++m_seq;
         if (c == nc - 1) {
           // ---- dV (warpgroup 0) / dK (warpgroup 1) of this key tile
-          const int kvn = it * nkt + kt;
           mbar_wait(dkv_full, kvn & 1);
           tc_fence_after();
           const int row = kt * 128 + sp * 32;
@@ -342,6 +348,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           else store_tile(t_lane + TM_DK, p.scale, (p.H + h) * 64, row, seq);
           if (lane == 0) mbar_arrive(dkv_free);
         }
+      }
       }
       // ---- dQ of the item
       mbar_wait(dq_full, it & 1);

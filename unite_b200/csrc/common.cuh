@@ -157,6 +157,12 @@ UB_DEVINL void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c
       : "memory");
 }
 
+// L2 prefetch of a tile (no smem, no completion tracking)
+UB_DEVINL void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // smem -> global tile store / fp32 reduce-add (bulk async group completion), clipped at the tensor bounds
 UB_DEVINL void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
@@ -290,6 +296,14 @@ UB_DEVINL void tma_load_2d_cg2(const CUtensorMap* m, uint32_t leader_bar_cluster
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// same, multicast: the box lands at this smem offset in every CTA of `mask`; each destination's bytes are counted on the
+// barrier at this offset in the leader of THAT destination's pair
+UB_DEVINL void tma_load_2d_cg2_mc(const CUtensorMap* m, uint32_t leader_bar_cluster_addr, void* dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar_cluster_addr), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 UB_DEVINL void tmem_alloc_cg2(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
                : "memory");
@@ -309,8 +323,7 @@ UB_DEVINL void umma_bf16_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, 
       : "memory");
 }
 // arrive (once) on the barrier at this smem offset in BOTH CTAs of the pair when the issued MMAs complete
-UB_DEVINL void umma_commit_cg2(uint64_t* bar) {
-  const uint16_t mask = 3;
+UB_DEVINL void umma_commit_cg2(uint64_t* bar, uint16_t mask = 3) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
                "h"(mask)
                : "memory");

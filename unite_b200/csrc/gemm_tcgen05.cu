@@ -44,24 +44,31 @@ struct GemmParams {
 
 // EPI : 0 = bias / activation (/ pre-activation copy), 1 = + fp32 residual (fp32 out), 2 = DGELU: * gelu'(aux) (bf16 out)
 // OUT32: C is fp32 (32-column slabs) or bf16 (64-column slabs); both give 128-byte staging rows
-// NCTA: 1 = one CTA per 128 x BN tile; 2 = CTA pair per 256 x BN tile
+// NCTA: 1 = one CTA per 128 x BN tile; 2 = CTA pair per 256 x BN tile; 4 = cluster of two pairs on a 512 x BN tile that
+//       share B: each CTA fetches a quarter of the B tile and TMA-multicasts it to the CTA of the same rank in the other pair
+//       (the mainloop is bound by L2 -> SM bytes: 24 KB instead of 32 KB per CTA and k-block)
 template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, bool OUT32, int NCTA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
             const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
-  constexpr int BN_L = BN / NCTA;            // rows of B resident in this CTA
+  constexpr int CG = NCTA >= 2 ? 2 : 1;      // CTAs per MMA (tcgen05 cta_group)
+  constexpr int NP = NCTA / CG;              // CTA pairs per cluster
+  constexpr int BN_L = BN / CG;              // rows of B resident in this CTA
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN_L * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // 256 or 512: power of two
-  constexpr uint32_t IDESC = umma_idesc_bf16(BM * NCTA, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  constexpr uint32_t IDESC = umma_idesc_bf16(BM * CG, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
   constexpr int CW = OUT32 ? 32 : 64;        // columns per epilogue slab
   constexpr int SLABS = (BN / 2) / CW;       // slabs per warp per tile
   static_assert(EPI != 1 || OUT32, "residual epilogue writes fp32");
   static_assert(EPI != 2 || !OUT32, "DGELU epilogue writes bf16");
-  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
-  const bool leader = cta_rank == 0;
+  const uint32_t cta_rank = NCTA >= 2 ? cluster_ctarank() : 0u;
+  const uint32_t pr = cta_rank & (CG - 1);          // rank inside the pair
+  const uint32_t pp = cta_rank / CG;                // pair inside the cluster
+  const uint32_t leader_rank = cta_rank - pr;
+  const bool leader = pr == 0;
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* epi_s = smem + STAGES * STAGE_BYTES;                       // [8 warps][2][4096], 1024-aligned
@@ -83,17 +90,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmC);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], NP);        // one commit per pair that reads (or multicasts into) the slot
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8 * NCTA);   // the leader's copy collects the epilogue warps of both CTAs
+      mbar_init(&tempty[i], 8 * CG);     // the leader's copy collects the epilogue warps of both CTAs
     }
     for (int i = 0; i < 16; ++i) mbar_init(&rbar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    if (NCTA == 2) {
+    if (NCTA >= 2) {
       tmem_alloc_cg2(tmem_slot, TMEM_COLS);
       tmem_relinquish_cg2();
     } else {
@@ -102,7 +109,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   }
   tc_fence_before();
-  if (NCTA == 2) cluster_sync(); else __syncthreads();
+  if (NCTA >= 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -120,7 +127,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int ks = w % p.splits;
       const int tile = w / p.splits;
       const int m0 = (tile / n_tiles) * (BM * NCTA) + (int)cta_rank * BM;      // this CTA's rows of A
-      const int n0 = (tile % n_tiles) * BN + (int)cta_rank * BN_L;             // this CTA's rows of B
+      const int n0 = (tile % n_tiles) * BN + (int)pr * BN_L;                   // this CTA's rows of B
       const int kb0 = ks * p.kb_per_split;
       const int kb1 = min(total_kb, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -128,9 +135,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) {
           uint8_t* sA = smem + stage * STAGE_BYTES;
           uint8_t* sB = sA + A_BYTES;
-          if (NCTA == 2) {
+          if (NCTA >= 2) {
             // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the whole pair
-            const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), 0);
+            const uint32_t lbar = mapa_u32(smem_u32(&full[stage]), leader_rank);
             if (leader) mbar_expect_tx(&full[stage], STAGE_BYTES * 2);
             if (A_MN) {
 #pragma unroll
@@ -138,7 +145,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             } else {
               tma_load_2d_cg2(&tmA, lbar, sA, kb * BK, m0);
             }
-            if (B_MN) {
+            if (NCTA == 4) {
+              // this CTA's quarter of the B tile (64 rows / one 64-wide MN chunk = 8 KB) lands in both pairs
+              const uint16_t mask = (uint16_t)((1u << pr) | (1u << (CG + pr)));
+              if (B_MN) tma_load_2d_cg2_mc(&tmB, lbar, sB + pp * 8192, n0 + (int)pp * 64, kb * BK, mask);
+              else tma_load_2d_cg2_mc(&tmB, lbar, sB + pp * 8192, kb * BK, n0 + (int)pp * 64, mask);
+            } else if (B_MN) {
 #pragma unroll
               for (int j = 0; j < BN_L / 64; ++j) tma_load_2d_cg2(&tmB, lbar, sB + j * 8192, n0 + j * 64, kb * BK);
             } else {
@@ -177,7 +189,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int ks = w % p.splits;
       const int kb0 = ks * p.kb_per_split;
       const int kb1 = min(total_kb, kb0 + p.kb_per_split);
-      if (NCTA == 2) mbar_wait_cluster(&tempty[as], aphase ^ 1); else mbar_wait(&tempty[as], aphase ^ 1);
+      if (NCTA >= 2) mbar_wait_cluster(&tempty[as], aphase ^ 1); else mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -193,13 +205,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // advance along K by 16 elements: 32 B inside the swizzle atom (K-major) or two 8-row groups (MN-major)
             const uint64_t ad = adesc + (uint64_t)(A_MN ? (k * 2048) >> 4 : (k * 32) >> 4);
             const uint64_t bd = bdesc + (uint64_t)(B_MN ? (k * 2048) >> 4 : (k * 32) >> 4);
-            if (NCTA == 2) umma_bf16_cg2(d_tmem, ad, bd, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (NCTA >= 2) umma_bf16_cg2(d_tmem, ad, bd, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
             else umma_bf16(d_tmem, ad, bd, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
-          if (NCTA == 2) umma_commit_cg2(&empty[stage]); else umma_commit(&empty[stage]);
+          if (NCTA >= 2) umma_commit_cg2(&empty[stage], (uint16_t)((1u << NCTA) - 1)); else umma_commit(&empty[stage]);
           if (kb == kb1 - 1) {
-            if (NCTA == 2) umma_commit_cg2(&tfull[as]); else umma_commit(&tfull[as]);
+            if (NCTA >= 2) umma_commit_cg2(&tfull[as], (uint16_t)(3u << leader_rank)); else umma_commit(&tfull[as]);
           }
         }
         __syncwarp();
@@ -368,7 +380,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (NCTA == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), 0)); else mbar_arrive(&tempty[as]);
+        if (NCTA >= 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), leader_rank)); else mbar_arrive(&tempty[as]);
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;
@@ -377,10 +389,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 
   tc_fence_before();
-  if (NCTA == 2) cluster_sync(); else __syncthreads();
+  if (NCTA >= 2) cluster_sync(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    if (NCTA == 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
+    if (NCTA >= 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -460,7 +472,7 @@ struct GemmMaps {
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, bool OUT32, int NCTA>
 static int launch_gemm_epi(const GemmMaps& m, const GemmParams& p, int grid, cudaStream_t stream) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / NCTA) * BK * 2) + EPI_BYTES + 2 * BN * 4 + (2 * STAGES + 4 + 16) * 8 + 16;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / (NCTA >= 2 ? 2 : 1)) * BK * 2) + EPI_BYTES + 2 * BN * 4 + (2 * STAGES + 4 + 16) * 8 + 16;
   static_assert(SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
   static bool configured = false;
   auto kern = gemm_kernel<BN, STAGES, A_MN, B_MN, EPI, OUT32, NCTA>;
@@ -486,6 +498,29 @@ static int launch_gemm_epi(const GemmMaps& m, const GemmParams& p, int grid, cud
   return check_launch("gemm_kernel");
 }
 
+// Clusters of 4 must sit inside one GPC: ask the driver how many fit at once (a persistent grid must be co-resident).
+static int max_clusters4() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  auto kern = gemm_kernel<256, 5, false, false, 0, false, 4>;
+  constexpr int SMEM = 5 * (BM * BK * 2 + 128 * BK * 2) + EPI_BYTES + 2 * 256 * 4 + (2 * 5 + 4 + 16) * 8 + 16;
+  int n = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) == cudaSuccess) {
+    cudaLaunchConfig_t q{};
+    q.gridDim = dim3(sm_count() / 4 * 4);
+    q.blockDim = dim3(GEMM_THREADS);
+    q.dynamicSmemBytes = SMEM;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 4; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    q.attrs = qa; q.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess) n = 0;
+  }
+  (void)cudaGetLastError();
+  cached = n > 0 ? n : 0;
+  return cached;
+}
+
 // epilogue variants actually used per operand-major combination (keeps the kernel count down):
 //   NT   (activations x weights): every variant          NN (dgrad, B = W): bf16 out, plain or DGELU
 //   TN   (wgrad, both MN-major) : fp32 out (accumulate)
@@ -508,6 +543,8 @@ static int launch_gemm(const GemmMaps& m, const GemmParams& p, int epi, bool out
 }
 
 }  // namespace ub
+
+extern "C" int ub_gemm_cluster4_capacity(void) { return ub::max_clusters4(); }
 
 extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                             void* C, int64_t ldc, int M, int N, int K, const ub_gemm_epilogue* ep_in, int split_k,
@@ -545,6 +582,7 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   // estimated time ~ waves x per-SM tile area / efficiency of the configuration (measured on B200: the 256-wide CTA-pair
   // tile has twice the operand reuse of the 128-wide tile and sustains ~1.3 PF; 1-CTA 256-wide ~1.15 PF; 128-wide ~0.75 PF)
   auto cost = [&](int bm, int bn, int units, double eff) {
+    if (eff <= 0.0) return 1e30;
     const long tiles = (long)((M + bm - 1) / bm) * ((N + bn - 1) / bn) * split_k;
     const long waves = (tiles + units - 1) / units;
     return (double)waves * (double)BM * bn / eff;
@@ -554,6 +592,18 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   int bn = 256, ncta = 1;
   if (N <= 128 || (c128 < c256 && c128 < c256x2)) bn = 128;
   else if (c256x2 <= c256) ncta = 2;
+  // two pairs sharing B by multicast: fewer L2 -> SM bytes per flop, but 512-row work items and whole clusters of 4 SMs
+  const int units4 = max_clusters4();
+  if (ncta == 2 && M >= 4 * BM && units4 > 0) {
+    static double eff4 = -1.0;
+    if (eff4 < 0) {
+      const char* e = getenv("UB_GEMM_EFF4");
+      eff4 = e ? atof(e) : 0.0;
+    }
+    // measured on B200: 9 % more throughput per SM (25 % fewer L2 -> SM bytes), but only 33 clusters of 4 fit (132 of 148
+    // SMs), a net loss of 3 % — so the cost model only picks it when told the per-SM gain (UB_GEMM_EFF4) outweighs that
+    if (force_ncta == 4 || (force_ncta == 0 && cost(4 * BM, 256, units4, eff4) < c256x2)) ncta = 4;
+  }
   if (force_ncta == 1) ncta = 1;
   if (force_ncta == 2 && bn == 256) ncta = 2;
 
@@ -584,12 +634,13 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   p.bias = ep.bias; p.row_scale = ep.row_scale; p.rows_per_scale = ep.rows_per_scale;
   p.act = ep.act; p.accumulate = ep.accumulate; p.has_aux_out = ep.aux_out != nullptr;
   const long total_work = (long)((M + BM * ncta - 1) / (BM * ncta)) * ((N + bn - 1) / bn) * split_k;
-  const int units = sms / ncta;
+  const int units = ncta == 4 ? units4 : sms / ncta;
   const int grid = (int)(total_work < units ? total_work : units) * ncta;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
 #define UB_GEMM_CASE(AMN, BMN)                                                                       \
   if ((a_mn_major != 0) == AMN && (b_mn_major != 0) == BMN) {                                         \
+    if (bn == 256 && ncta == 4) return launch_gemm<256, 5, AMN, BMN, 4>(m, p, epi, out32, grid, st);  \
     if (bn == 256 && ncta == 2) return launch_gemm<256, 5, AMN, BMN, 2>(m, p, epi, out32, grid, st);  \
     return bn == 256 ? launch_gemm<256, 3, AMN, BMN, 1>(m, p, epi, out32, grid, st)                   \
                      : launch_gemm<128, 5, AMN, BMN, 1>(m, p, epi, out32, grid, st);                  \

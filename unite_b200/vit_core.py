@@ -14,6 +14,7 @@ Data layout in HBM (M = B * N_tokens rows, D = embed dim):
 Weights are read from the arena's bf16 shadow; gradients are red.add-ed into the arena's fp32 grad buffer.
 """
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -22,6 +23,11 @@ from . import ops
 from .arena import ParamArena
 
 BF16, F32 = torch.bfloat16, torch.float32
+
+
+# measured on B200 (round 1): no gain — every GEMM is a persistent one-CTA-per-SM grid, so two of them cannot share SMs and
+# the tails they could fill are short; kept as an option (UB_SIDE_WGRAD=1)
+_SIDE_WGRAD = os.environ.get("UB_SIDE_WGRAD", "0") == "1"
 
 
 def _splits_for(out_rows: int, out_cols: int, sms: int) -> int:
@@ -56,11 +62,14 @@ class TrunkWorkspace:
             self.layers.append(L)
         if save:  # backward temporaries, shared by all layers
             self.dx = torch.empty(M, D, device=dev, dtype=F32)
-            self.dxs = torch.empty(M, D, device=dev, dtype=BF16)
-            self.d_pre = torch.empty(M, hidden, device=dev, dtype=BF16)
+            # consumed by the weight-gradient GEMMs, which run one layer behind on a side stream: two copies (layer parity)
+            self.dxs_m = [torch.empty(M, D, device=dev, dtype=BF16) for _ in range(2)]     # gradient entering the MLP branch
+            self.dxs_a = [torch.empty(M, D, device=dev, dtype=BF16) for _ in range(2)]     # ... the attention branch
+            self.d_pre2 = [torch.empty(M, hidden, device=dev, dtype=BF16) for _ in range(2)]
+            self.dqkv2 = [torch.empty(M, 3 * D, device=dev, dtype=BF16) for _ in range(2)]
+            self.dxs, self.d_pre, self.dqkv = self.dxs_m[0], self.d_pre2[0], self.dqkv2[0]
             self.d_h = torch.empty(M, D, device=dev, dtype=BF16)
             self.d_o = torch.empty(M, D, device=dev, dtype=BF16)
-            self.dqkv = torch.empty(M, 3 * D, device=dev, dtype=BF16)
             self.d_ws = torch.empty(B, H, N, device=dev, dtype=F32)
 
     def layer(self, l):
@@ -80,6 +89,11 @@ class ViTTrunk:
         self.scale = 64 ** -0.5
         self.sms = ops.lib.ub_sm_count() if torch.cuda.is_available() else 148
         self._ws: Dict = {}
+
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.arena.device)
+        return self._side
 
     # -- parameter access ---------------------------------------------------------------------
     def w(self, name):       # bf16 shadow (GEMM operand)
@@ -156,53 +170,85 @@ class ViTTrunk:
 
         tap_grads[l](dx_in, dxs_out, row_scale, dsum) must add the gradient arriving at the OUTPUT of block l into the
         residual-gradient buffer ws.dx (dx_in is None when nothing has been accumulated yet), emit
-        ws.dxs = bf16(ws.dx * row_scale) and accumulate its column sums (block l's fc2 bias gradient) into dsum.  If dx_init is True, ws.dx already holds the gradient wrt the last
+        dxs_out = bf16(ws.dx * row_scale) and accumulate its column sums (block l's fc2 bias gradient) into dsum.  If dx_init is True, ws.dx already holds the gradient wrt the last
         block's output."""
         N, D = ws.N, self.D
         dp = ws.dp
         have_dx = dx_init
         nl = ws.n_layers
+        # Weight gradients are off the critical path (nothing reads them before the optimizer): they are issued on a side
+        # stream so their CTAs fill the SMs the dgrad / attention / LayerNorm chain leaves idle (wave tails, small grids).
+        side = self._side_stream() if (_SIDE_WGRAD and ws.dx.is_cuda) else None
+        main = torch.cuda.current_stream() if side is not None else None
+        side_done = {}
+
+        def wgrad(dy, x_in, gw):
+            if side is None:
+                return self._wgrad(dy, x_in, gw)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                self._wgrad(dy, x_in, gw)
+
+        def block_final(l):
+            if on_block_done is not None:
+                on_block_done(l)     # every gradient of block l is final: its arena range can be all-reduced
+
         for l in reversed(range(nl)):
             L = ws.layer(l)
             b = f"blocks.{l}."
+            par = l & 1
+            dxs_m, dxs_a, d_pre, dqkv = ws.dxs_m[par], ws.dxs_a[par], ws.d_pre2[par], ws.dqkv2[par]
+            if side is not None and (l + 2) in side_done:
+                main.wait_event(side_done[l + 2])        # the scratch of this parity is free again
+                block_final(l + 2)
             s_mlp = None if dp is None else dp[l, 1]
             s_att = None if dp is None else dp[l, 0]
-            # the producer of ws.dxs also accumulates its column sums = the bias gradient of the Linear it feeds
+            # the producer of dxs also accumulates its column sums = the bias gradient of the Linear it feeds
             if l in tap_grads:
-                tap_grads[l](ws.dx if have_dx else None, ws.dxs, s_mlp, self.g(b + "mlp.fc2.bias"))
+                tap_grads[l](ws.dx if have_dx else None, dxs_m, s_mlp, self.g(b + "mlp.fc2.bias"))
                 have_dx = True
             elif l == nl - 1:
                 assert have_dx, "no gradient reaches the last block"
-                ops.cast_scale_bf16(ws.dx, ws.dxs, s_mlp, N)
-                ops.colsum_bf16(ws.dxs, self.g(b + "mlp.fc2.bias"))
+                ops.cast_scale_bf16(ws.dx, dxs_m, s_mlp, N)
+                ops.colsum_bf16(dxs_m, self.g(b + "mlp.fc2.bias"))
             # ---- MLP branch: x_out = x_mid + s * (gelu(h2 W1^T + b1) W2^T + b2)
-            ops.gemm(ws.dxs, self.w(b + "mlp.fc2.weight"), ws.d_pre, b_t=True, act=ops.UB_ACT_DGELU, aux_in=L.pre)
-            self._wgrad(ws.dxs, L.act, self.g(b + "mlp.fc2.weight"))
-            ops.gemm(ws.d_pre, self.w(b + "mlp.fc1.weight"), ws.d_h, b_t=True)
-            self._wgrad(ws.d_pre, L.h2, self.g(b + "mlp.fc1.weight"))
-            ops.colsum_bf16(ws.d_pre, self.g(b + "mlp.fc1.bias"))
-            ops.layernorm_bwd(ws.d_h, L.x_mid, self.p(b + "norm2.weight"), self.eps, ws.dx, ws.dx, ws.dxs, s_att, N,
+            # (each side-stream GEMM is enqueued AFTER the critical-path kernel it runs beside, so the latter gets the SMs first)
+            ops.gemm(dxs_m, self.w(b + "mlp.fc2.weight"), d_pre, b_t=True, act=ops.UB_ACT_DGELU, aux_in=L.pre)
+            wgrad(dxs_m, L.act, self.g(b + "mlp.fc2.weight"))
+            ops.gemm(d_pre, self.w(b + "mlp.fc1.weight"), ws.d_h, b_t=True)
+            wgrad(d_pre, L.h2, self.g(b + "mlp.fc1.weight"))
+            ops.colsum_bf16(d_pre, self.g(b + "mlp.fc1.bias"))
+            ops.layernorm_bwd(ws.d_h, L.x_mid, self.p(b + "norm2.weight"), self.eps, ws.dx, ws.dx, dxs_a, s_att, N,
                               self.g(b + "norm2.weight"), self.g(b + "norm2.bias"), dsum=self.g(b + "attn.proj.bias"))
             # ---- attention branch: x_mid = x_in + s * (attn(h1) Wp^T + bp)
-            ops.gemm(ws.dxs, self.w(b + "attn.proj.weight"), ws.d_o, b_t=True)
-            self._wgrad(ws.dxs, L.o, self.g(b + "attn.proj.weight"))
-            ops.attn_bwd(L.qkv, L.o, ws.d_o, L.lse, ws.d_ws, ws.dqkv, ws.B, N, self.H, self.scale)
-            ops.gemm(ws.dqkv, self.w(b + "attn.qkv.weight"), ws.d_h, b_t=True)
-            self._wgrad(ws.dqkv, L.h1, self.g(b + "attn.qkv.weight"))
+            ops.gemm(dxs_a, self.w(b + "attn.proj.weight"), ws.d_o, b_t=True)
+            wgrad(dxs_a, L.o, self.g(b + "attn.proj.weight"))
+            ops.attn_bwd(L.qkv, L.o, ws.d_o, L.lse, ws.d_ws, dqkv, ws.B, N, self.H, self.scale)
+            ops.gemm(dqkv, self.w(b + "attn.qkv.weight"), ws.d_h, b_t=True)
+            wgrad(dqkv, L.h1, self.g(b + "attn.qkv.weight"))
             # q_bias | (always-zero k gap) | v_bias are one contiguous 3D span of the gradient arena: one column-sum pass
             # over all of dqkv, then clear the gap (the key bias is structurally zero, modeling_finetune.py:104)
             gq = self.qkv_bias_grad(l)
-            ops.colsum_bf16(ws.dqkv, gq)
+            ops.colsum_bf16(dqkv, gq)
             gq[D:2 * D].zero_()
             # next consumer of dxs: block l-1's MLP branch (unless a tap re-emits it) or the patch embedding
             emit = (l - 1) not in tap_grads
             s_next = None if (dp is None or l == 0) else dp[l - 1, 1]
             next_bias = self.g("patch_embed.proj.bias") if l == 0 else self.g(f"blocks.{l - 1}.mlp.fc2.bias")
             ops.layernorm_bwd(ws.d_h, ws.x_at(l), self.p(b + "norm1.weight"), self.eps, ws.dx, ws.dx,
-                              ws.dxs if emit else None, s_next, N, self.g(b + "norm1.weight"), self.g(b + "norm1.bias"),
-                              dsum=next_bias if emit else None)
-            if on_block_done is not None:
-                on_block_done(l)     # every gradient of block l is final: its arena range can be all-reduced
+                              ws.dxs_m[(l - 1) & 1] if emit else None, s_next, N, self.g(b + "norm1.weight"),
+                              self.g(b + "norm1.bias"), dsum=next_bias if emit else None)
+            if side is not None:
+                side_done[l] = torch.cuda.Event()
+                side_done[l].record(side)
+            else:
+                block_final(l)
+        if side is not None:
+            main.wait_stream(side)
+            for l in reversed(range(min(2, nl))):
+                block_final(l)
         # ---- patch embedding (Conv3d as GEMM): only weight and bias gradients exist
         gw = self.g("patch_embed.proj.weight")
-        self._wgrad(ws.dxs, ws.patches, gw.view(D, -1))
+        self._wgrad(ws.dxs_m[1], ws.patches, gw.view(D, -1))
