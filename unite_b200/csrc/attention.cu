@@ -104,6 +104,7 @@ UB_DEVINL void store_acc_bf16(uint8_t* s_tile, int warp_row0, int lane, const fl
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o,
                                                        float* __restrict__ lse, int S, int H, float scale) {
+  pdl_grid_sync();
   __shared__ __align__(1024) uint8_t sQ[TQ * 128];
   __shared__ __align__(1024) uint8_t sK[2][TQ * 128];
   __shared__ __align__(1024) uint8_t sV[2][TQ * 128];
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ D,
                                      int n_rows, int S, int H) {
+  pdl_grid_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n_rows) return;
@@ -253,6 +255,7 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __r
 __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
                                                            const float* __restrict__ lse, const float* __restrict__ Dv,
                                                            bf16* __restrict__ dqkv, int S, int H, float scale) {
+  pdl_grid_sync();
   extern __shared__ __align__(1024) uint8_t smem_dkv[];
   uint8_t* sK = smem_dkv;                      // 8 KB (reused to stage dK)
   uint8_t* sV = sK + TQ * 128;                 // 8 KB (reused to stage dV)
@@ -378,6 +381,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const bf16* __restric
 __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ d_o,
                                                           const float* __restrict__ lse, const float* __restrict__ Dv,
                                                           bf16* __restrict__ dqkv, int S, int H, float scale) {
+  pdl_grid_sync();
   extern __shared__ __align__(1024) uint8_t smem_dq[];
   uint8_t* sQ = smem_dq;                 // 8 KB (reused to stage dQ)
   uint8_t* sdO = sQ + TQ * 128;          // 8 KB
@@ -483,6 +487,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const bf16* __restrict
 //   out[seq, j] = 1/H * sum_h softmax_k(q_cls . k / sqrt(d))[j+1],   j in [0, S-1)
 // ------------------------------------------------------------------------------------------------
 __global__ void cls_attn_kernel(const bf16* __restrict__ qkv, float* __restrict__ out, int S, int H, float scale) {
+  pdl_grid_sync();
   extern __shared__ float s_probs[];  // [H][S]
   const int seq = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ld = 3 * (int64_t)H * HD;
@@ -560,7 +565,7 @@ extern "C" int ub_attn_fwd(const void* qkv, void* o, float* lse, int n_seq, int 
   if (use_tc && lse == nullptr && S <= 240) return   // (K and V for NK <= 240 padded keys fit the 227 KB smem budget twice)
     launch_attn_fwd_tc(qkv, o, n_seq, S, H, scale, (cudaStream_t)stream);
   dim3 grid((S + TQ - 1) / TQ, H, n_seq);
-  attn_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)o, lse, S, H, scale);
+  UB_LAUNCH(attn_fwd_kernel, grid, 128, 0, (cudaStream_t)stream, (const bf16*)qkv, (bf16*)o, lse, S, H, scale);
   return check_launch("attn_fwd_kernel");
 }
 
@@ -570,7 +575,7 @@ extern "C" int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, cons
   UB_REQUIRE(n_seq > 0 && S > 0 && H > 0, "attn_bwd: bad shape n_seq=%d S=%d H=%d", n_seq, S, H);
   cudaStream_t st = (cudaStream_t)stream;
   const int n_rows = n_seq * S;
-  attn_bwd_prep_kernel<<<(n_rows + 7) / 8, 256, 0, st>>>((const bf16*)o, (const bf16*)d_o, D_ws, n_rows, S, H);
+  UB_LAUNCH(attn_bwd_prep_kernel, (n_rows + 7) / 8, 256, 0, st, (const bf16*)o, (const bf16*)d_o, D_ws, n_rows, S, H);
   if (check_launch("attn_bwd_prep_kernel")) return 1;
   // short sequences (the student's <= 320 visible tokens): single-pass tcgen05 / TMEM kernel
   static int use_tc = -1;
@@ -589,9 +594,9 @@ extern "C" int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, cons
     UB_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, "attn_bwd: cudaFuncSetAttribute failed");
     configured = true;
   }
-  attn_bwd_dkv_kernel<<<grid, 128, SMEM_DKV, st>>>((const bf16*)qkv, (const bf16*)d_o, lse, D_ws, (bf16*)dqkv, S, H, scale);
+  UB_LAUNCH(attn_bwd_dkv_kernel, grid, 128, SMEM_DKV, st, (const bf16*)qkv, (const bf16*)d_o, lse, D_ws, (bf16*)dqkv, S, H, scale);
   if (check_launch("attn_bwd_dkv_kernel")) return 1;
-  attn_bwd_dq_kernel<<<grid, 128, SMEM_DQ, st>>>((const bf16*)qkv, (const bf16*)d_o, lse, D_ws, (bf16*)dqkv, S, H, scale);
+  UB_LAUNCH(attn_bwd_dq_kernel, grid, 128, SMEM_DQ, st, (const bf16*)qkv, (const bf16*)d_o, lse, D_ws, (bf16*)dqkv, S, H, scale);
   return check_launch("attn_bwd_dq_kernel");
 }
 
@@ -600,6 +605,6 @@ extern "C" int ub_cls_attn(const void* qkv, float* out, int n_seq, int S, int H,
   UB_REQUIRE(H >= 1 && H <= 32 && S >= 2, "cls_attn: unsupported H=%d S=%d", H, S);
   const size_t smem = (size_t)H * S * sizeof(float);
   UB_REQUIRE(smem <= 48 * 1024, "cls_attn: sequence too long for the CLS-row kernel (S=%d)", S);
-  cls_attn_kernel<<<n_seq, H * 32, smem, (cudaStream_t)stream>>>((const bf16*)qkv, out, S, H, scale);
+  UB_LAUNCH(cls_attn_kernel, n_seq, H * 32, smem, (cudaStream_t)stream, (const bf16*)qkv, out, S, H, scale);
   return check_launch("cls_attn_kernel");
 }

@@ -105,6 +105,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();     // everything above overlapped the previous kernel's tail; global memory is touched only below
   const int n_items = p.n_seq * p.H;
   const int nkt = p.nkt, nc = p.nc, total = p.nkt * p.nc;
   constexpr uint32_t TM_DV = 192, TM_DK = 256, TM_DQ = 320;
@@ -396,7 +397,7 @@ int launch_attn_bwd_tc(const void* qkv, const void* d_o, const float* lse, const
   }
   const int items = n_seq * H;
   const int grid = items < sm_count() ? items : sm_count();
-  attn_bwd_tc_kernel<<<grid, ABT_THREADS, ABT_SMEM, stream>>>(tq, tkv, tdo, tout, p);
+  UB_LAUNCH(attn_bwd_tc_kernel, grid, ABT_THREADS, ABT_SMEM, stream, tq, tkv, tdo, tout, p);
   return check_launch("attn_bwd_tc_kernel");
 }
 

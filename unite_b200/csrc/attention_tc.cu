@@ -82,6 +82,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_grid_sync();     // everything above overlapped the previous kernel's tail; global memory is touched only below
   const int n_items = p.n_seq * p.H;
   constexpr int SM_WARP0 = NKT ? 4 : 2;    // first softmax warp
 
@@ -414,7 +415,7 @@ int launch_attn_fwd_tc(const void* qkv, void* o, int n_seq, int S, int H, float 
       UB_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(attn_fwd_tc<208> smem=%d): %s", smem, cudaGetErrorString(e));
       configured208 = smem;
     }
-    attn_fwd_tc_kernel<208><<<grid, 384, smem, stream>>>(tq, tkv, to, p);
+    UB_LAUNCH(attn_fwd_tc_kernel<208>, grid, 384, smem, stream, tq, tkv, to, p);
     return check_launch("attn_fwd_tc_kernel<208>");
   }
   static int configured = 0;
@@ -423,7 +424,7 @@ int launch_attn_fwd_tc(const void* qkv, void* o, int n_seq, int S, int H, float 
     UB_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(attn_fwd_tc smem=%d): %s", smem, cudaGetErrorString(e));
     configured = smem;
   }
-  attn_fwd_tc_kernel<0><<<grid, ATC_THREADS, smem, stream>>>(tq, tkv, to, p);
+  UB_LAUNCH(attn_fwd_tc_kernel<0>, grid, ATC_THREADS, smem, stream, tq, tkv, to, p);
   return check_launch("attn_fwd_tc_kernel");
 }
 

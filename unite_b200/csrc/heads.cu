@@ -16,6 +16,7 @@ namespace ub {
 
 // out[b, d] = mean_n x[b, n, d];  grid (D/128, B), 128 threads, each thread one column, rows strided by 8 sub-rows
 __global__ void __launch_bounds__(256) meanpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int D) {
+  pdl_grid_sync();
   __shared__ float s_part[8][32];
   const int b = blockIdx.y, d = blockIdx.x * 32 + (threadIdx.x & 31), rg = threadIdx.x >> 5;
   float acc = 0.f;
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__(256) meanpool_fwd_kernel(const float* __restri
 // dx[b, n, :] = g[b, :] / N   (fp32, 128-bit stores)
 __global__ void __launch_bounds__(256) meanpool_bwd_kernel(const float4* __restrict__ g, float4* __restrict__ dx, int N, int D4,
                                                            long total4, float invN) {
+  pdl_grid_sync();
   for (long id = (long)blockIdx.x * blockDim.x + threadIdx.x; id < total4; id += (long)gridDim.x * blockDim.x) {
     const int d4 = (int)(id % D4);
     const long b = id / ((long)N * D4);
@@ -49,6 +51,7 @@ __global__ void __launch_bounds__(256) meanpool_bwd_kernel(const float4* __restr
 __global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                                const float* __restrict__ bias, float* __restrict__ out, int B,
                                                                int C, int D) {
+  pdl_grid_sync();
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (w >= B * C) return;
   const int b = w / C, c = w % C;
@@ -62,6 +65,7 @@ __global__ void __launch_bounds__(256) linear_small_fwd_kernel(const float* __re
 __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                                const float* __restrict__ dout, float* __restrict__ dx,
                                                                float* __restrict__ dW, float* __restrict__ db, int B, int C, int D) {
+  pdl_grid_sync();
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d < D) {
     if (dx != nullptr) {
@@ -91,6 +95,7 @@ __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const float* __re
 __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict__ logits, const int* __restrict__ labels,
                                                          const float* __restrict__ weights, float scale, float* __restrict__ loss_acc,
                                                          float* __restrict__ dlogits, int B, int C) {
+  pdl_grid_sync();
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   const float* l = logits + (int64_t)b * C;
@@ -111,6 +116,7 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
 // probs[b, c] = mean_t softmax_c(100 * <img[b*T+t]/|.|, txt[c]/|.|>)   one block per clip, one warp per frame, C <= 32*? (loop)
 __global__ void __launch_bounds__(256) clip_zero_shot_kernel(const float* __restrict__ img, const float* __restrict__ txt,
                                                              float* __restrict__ probs, int T, int C, int D) {
+  pdl_grid_sync();
   extern __shared__ float s_acc[];   // [C] accumulated probabilities, then [warps][C] similarities
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   float* sim = s_acc + C + warp * C;
@@ -150,6 +156,7 @@ __global__ void __launch_bounds__(256) pseudo_label_fusion_kernel(const float* _
                                                                   float thr, int conf_weighted, float* __restrict__ msp_out,
                                                                   int* __restrict__ pseudo, uint8_t* __restrict__ sel,
                                                                   float* __restrict__ weight, int B, int C) {
+  pdl_grid_sync();
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   const float* l = logits + (int64_t)b * C;
@@ -189,7 +196,7 @@ using namespace ub;
 extern "C" int ub_meanpool_fwd(const float* x, float* out, int B, int N, int D, void* stream) {
   UB_REQUIRE(x && out && B > 0 && N > 0 && D > 0, "meanpool_fwd: bad arguments");
   dim3 grid((D + 31) / 32, B);
-  meanpool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out, N, D);
+  UB_LAUNCH(meanpool_fwd_kernel, grid, 256, 0, (cudaStream_t)stream, x, out, N, D);
   return check_launch("meanpool_fwd_kernel");
 }
 
@@ -198,28 +205,28 @@ extern "C" int ub_meanpool_bwd(const float* g, float* dx, int B, int N, int D, v
   const long total4 = (long)B * N * (D / 4);
   long blocks = (total4 + 255) / 256;
   const long cap = (long)sm_count() * 16;
-  meanpool_bwd_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>((const float4*)g, (float4*)dx, N, D / 4, total4,
+  UB_LAUNCH(meanpool_bwd_kernel, (int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream, (const float4*)g, (float4*)dx, N, D / 4, total4,
                                                                                            1.0f / (float)N);
   return check_launch("meanpool_bwd_kernel");
 }
 
 extern "C" int ub_linear_small_fwd(const float* x, const float* W, const float* bias, float* out, int B, int C, int D, void* stream) {
   UB_REQUIRE(x && W && out && B > 0 && C > 0 && D > 0, "linear_small_fwd: bad arguments");
-  linear_small_fwd_kernel<<<(B * C + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, W, bias, out, B, C, D);
+  UB_LAUNCH(linear_small_fwd_kernel, (B * C + 7) / 8, 256, 0, (cudaStream_t)stream, x, W, bias, out, B, C, D);
   return check_launch("linear_small_fwd_kernel");
 }
 
 extern "C" int ub_linear_small_bwd(const float* x, const float* W, const float* dout, float* dx, float* dW, float* db, int B, int C,
                                    int D, void* stream) {
   UB_REQUIRE(x && W && dout && B > 0 && C > 0 && C <= 256 && D > 0, "linear_small_bwd: bad arguments (C <= 256)");
-  linear_small_bwd_kernel<<<(D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, W, dout, dx, dW, db, B, C, D);
+  UB_LAUNCH(linear_small_bwd_kernel, (D + 255) / 256, 256, 0, (cudaStream_t)stream, x, W, dout, dx, dW, db, B, C, D);
   return check_launch("linear_small_bwd_kernel");
 }
 
 extern "C" int ub_softmax_ce(const float* logits, const int* labels, const float* weights, float scale, float* loss_acc,
                              float* dlogits, int B, int C, void* stream) {
   UB_REQUIRE(logits && labels && B > 0 && C > 0, "softmax_ce: bad arguments");
-  softmax_ce_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(logits, labels, weights, scale, loss_acc, dlogits, B, C);
+  UB_LAUNCH(softmax_ce_kernel, (B + 7) / 8, 256, 0, (cudaStream_t)stream, logits, labels, weights, scale, loss_acc, dlogits, B, C);
   return check_launch("softmax_ce_kernel");
 }
 
@@ -228,14 +235,14 @@ extern "C" int ub_clip_zero_shot(const float* img_feat, const float* text_feat, 
   UB_REQUIRE(img_feat && text_feat && probs && B > 0 && T > 0 && C > 0 && D > 0, "clip_zero_shot: bad arguments");
   const size_t smem = (size_t)(C + 8 * C) * sizeof(float);
   UB_REQUIRE(smem <= 48 * 1024, "clip_zero_shot: too many classes (C=%d)", C);
-  clip_zero_shot_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(img_feat, text_feat, probs, T, C, D);
+  UB_LAUNCH(clip_zero_shot_kernel, B, 256, smem, (cudaStream_t)stream, img_feat, text_feat, probs, T, C, D);
   return check_launch("clip_zero_shot_kernel");
 }
 
 extern "C" int ub_pseudo_label_fusion(const float* logits_full, const float* clip_probs, float threshold, int conf_weighted,
                                       float* msp, int* pseudo, uint8_t* sel, float* weight, int B, int C, void* stream) {
   UB_REQUIRE(logits_full && clip_probs && msp && pseudo && sel && weight && B > 0 && C > 0, "pseudo_label_fusion: bad arguments");
-  pseudo_label_fusion_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(logits_full, clip_probs, threshold, conf_weighted, msp,
+  UB_LAUNCH(pseudo_label_fusion_kernel, (B + 7) / 8, 256, 0, (cudaStream_t)stream, logits_full, clip_probs, threshold, conf_weighted, msp,
                                                                             pseudo, sel, weight, B, C);
   return check_launch("pseudo_label_fusion_kernel");
 }

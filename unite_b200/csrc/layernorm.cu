@@ -104,6 +104,7 @@ struct LnFwdArgs {
 
 template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   constexpr int nv = NV;
   const int wpb = blockDim.x >> 5;
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(256) teacher_embed_ln_kernel(const float* __re
                                                                const float* __restrict__ pos, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float* __restrict__ out,
                                                                int frames, int P, int D, float eps) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   constexpr int nv = NV;
   const int wpb = blockDim.x >> 5;
@@ -206,6 +208,7 @@ UB_DEVINL void block_col_reduce_atomic(const RowT<NV>& part, float* s_buf, float
 
 template <int NV>
 __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const LnBwdArgs a) {
+  pdl_grid_sync();
   extern __shared__ float s_red[];  // [warps][D]
   const int lane = threadIdx.x & 31;
   constexpr int nv = NV;
@@ -270,6 +273,7 @@ __global__ void __launch_bounds__(256) dec_tail_fwd_kernel(const float* __restri
                                                            const float* __restrict__ beta, float* __restrict__ out,
                                                            const float* __restrict__ tgt, float* __restrict__ loss_acc,
                                                            float loss_scale, int rows, int D, float eps) {
+  pdl_grid_sync();
   __shared__ float s_loss[8];
   const int lane = threadIdx.x & 31;
   constexpr int nv = NV;
@@ -316,6 +320,7 @@ __global__ void __launch_bounds__(256) dec_tail_bwd_kernel(const float* __restri
                                                            const float* __restrict__ beta, const float* __restrict__ go,
                                                            float go_scale, bf16* __restrict__ dy_out, float* __restrict__ dgamma,
                                                            float* __restrict__ dbeta, int rows, int D, float eps) {
+  pdl_grid_sync();
   extern __shared__ float s_red[];
   const int lane = threadIdx.x & 31;
   constexpr int nv = NV;
@@ -368,6 +373,7 @@ __global__ void __launch_bounds__(256) dec_tail_bwd_kernel(const float* __restri
 // x[row] /= ||x[row]||   (teacher targets, clip.py:173)
 template <int NV>
 __global__ void __launch_bounds__(256) l2norm_rows_kernel(float* __restrict__ x, int rows, int D) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   constexpr int nv = NV;
   const int wpb = blockDim.x >> 5;
@@ -382,11 +388,11 @@ __global__ void __launch_bounds__(256) l2norm_rows_kernel(float* __restrict__ x,
 
 #define UB_LN_DISPATCH(D, KERNEL, GRID, SMEM, STREAM, ...)                                   \
   switch ((D) >> 7) {                                                                         \
-    case 1: KERNEL<1><<<GRID, 256, SMEM, STREAM>>>(__VA_ARGS__); break;                       \
-    case 2: KERNEL<2><<<GRID, 256, SMEM, STREAM>>>(__VA_ARGS__); break;                       \
-    case 4: KERNEL<4><<<GRID, 256, SMEM, STREAM>>>(__VA_ARGS__); break;                       \
-    case 6: KERNEL<6><<<GRID, 256, SMEM, STREAM>>>(__VA_ARGS__); break;                       \
-    case 8: KERNEL<8><<<GRID, 256, SMEM, STREAM>>>(__VA_ARGS__); break;                       \
+    case 1: UB_LAUNCH(KERNEL<1>, GRID, 256, SMEM, STREAM, __VA_ARGS__); break;                       \
+    case 2: UB_LAUNCH(KERNEL<2>, GRID, 256, SMEM, STREAM, __VA_ARGS__); break;                       \
+    case 4: UB_LAUNCH(KERNEL<4>, GRID, 256, SMEM, STREAM, __VA_ARGS__); break;                       \
+    case 6: UB_LAUNCH(KERNEL<6>, GRID, 256, SMEM, STREAM, __VA_ARGS__); break;                       \
+    case 8: UB_LAUNCH(KERNEL<8>, GRID, 256, SMEM, STREAM, __VA_ARGS__); break;                       \
     default: break;                                                                           \
   }
 

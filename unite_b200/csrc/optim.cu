@@ -12,6 +12,7 @@ namespace ub {
 
 // sum of squares of a flat fp32 buffer, accumulated into out[0] with one red.add per block
 __global__ void __launch_bounds__(256) sumsq_kernel(const float4* __restrict__ g, long n4, float* __restrict__ out) {
+  pdl_grid_sync();
   __shared__ float s_part[8];
   float acc = 0.f;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
@@ -34,6 +35,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, cons
                                                     float4* __restrict__ v, uint2* __restrict__ w_bf16, long n4, long n4_decay,
                                                     float lr, float wd, float beta1, float beta2, float eps, float bc1,
                                                     float bc2_sqrt, float grad_scale) {
+  pdl_grid_sync();
   const float step_size = lr / bc1;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
     float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
@@ -64,6 +66,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, cons
 __global__ void __launch_bounds__(256) adamw_dev_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
                                                         float4* __restrict__ v, uint2* __restrict__ w_bf16, long n4, long n4_decay,
                                                         const float* __restrict__ hyper) {
+  pdl_grid_sync();
   const float lr = hyper[0], wd = hyper[1], beta1 = hyper[2], beta2 = hyper[3], eps = hyper[4], bc1 = hyper[5], bc2_sqrt = hyper[6],
               grad_scale = hyper[7];
   const float step_size = lr / bc1;
@@ -91,6 +94,7 @@ __global__ void __launch_bounds__(256) adamw_dev_kernel(float4* __restrict__ p, 
 }
 
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ out, long n4) {
+  pdl_grid_sync();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
     const float4 v = x[i];
     uint2 o;
@@ -112,7 +116,7 @@ using namespace ub;
 
 extern "C" int ub_sumsq(const float* g, int64_t n, float* out, void* stream) {
   UB_REQUIRE(g && out && n > 0 && n % 4 == 0, "sumsq: n=%lld must be a positive multiple of 4", (long long)n);
-  sumsq_kernel<<<flat_grid4(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)g, n / 4, out);
+  UB_LAUNCH(sumsq_kernel, flat_grid4(n / 4), 256, 0, (cudaStream_t)stream, (const float4*)g, n / 4, out);
   return check_launch("sumsq_kernel");
 }
 
@@ -124,7 +128,7 @@ extern "C" int ub_adamw(float* p, const float* g, float* m, float* v, void* w_bf
   UB_REQUIRE(step >= 1, "adamw: step must be >= 1");
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2 = 1.0f - powf(beta2, (float)step);
-  adamw_kernel<<<flat_grid4(n / 4), 256, 0, (cudaStream_t)stream>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v,
+  UB_LAUNCH(adamw_kernel, flat_grid4(n / 4), 256, 0, (cudaStream_t)stream, (float4*)p, (const float4*)g, (float4*)m, (float4*)v,
                                                                    (uint2*)w_bf16, n / 4, n_decay / 4, lr, wd, beta1, beta2, eps,
                                                                    bc1, sqrtf(bc2), grad_scale);
   return check_launch("adamw_kernel");
@@ -135,13 +139,13 @@ extern "C" int ub_adamw_dev(float* p, const float* g, float* m, float* v, void* 
   UB_REQUIRE(p && g && m && v && hyper, "adamw_dev: null pointer");
   UB_REQUIRE(n > 0 && n % 4 == 0 && n_decay % 4 == 0 && n_decay >= 0 && n_decay <= n,
              "adamw_dev: n=%lld and n_decay=%lld must be multiples of 4", (long long)n, (long long)n_decay);
-  adamw_dev_kernel<<<flat_grid4(n / 4), 256, 0, (cudaStream_t)stream>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v,
+  UB_LAUNCH(adamw_dev_kernel, flat_grid4(n / 4), 256, 0, (cudaStream_t)stream, (float4*)p, (const float4*)g, (float4*)m, (float4*)v,
                                                                        (uint2*)w_bf16, n / 4, n_decay / 4, hyper);
   return check_launch("adamw_dev_kernel");
 }
 
 extern "C" int ub_cast_bf16(const float* x, void* out, int64_t n, void* stream) {
   UB_REQUIRE(x && out && n > 0 && n % 4 == 0, "cast_bf16: n=%lld must be a positive multiple of 4", (long long)n);
-  cast_bf16_kernel<<<flat_grid4(n / 4), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)out, n / 4);
+  UB_LAUNCH(cast_bf16_kernel, flat_grid4(n / 4), 256, 0, (cudaStream_t)stream, (const float4*)x, (uint2*)out, n / 4);
   return check_launch("cast_bf16_kernel");
 }

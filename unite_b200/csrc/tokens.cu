@@ -21,6 +21,7 @@ namespace ub {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int T,
                                                        int H, int W, int tub, long total_runs) {
+  pdl_grid_sync();
   const int gh = H / 16, gw = W / 16, Tp = T / tub;
   const int runs_per_tok = 3 * tub * 16;
   for (long id = (long)blockIdx.x * blockDim.x + threadIdx.x; id < total_runs; id += (long)gridDim.x * blockDim.x) {
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(128) mask_select_kernel(const float* __restric
                                                           uint8_t* __restrict__ mask, int* __restrict__ vis_idx,
                                                           int* __restrict__ tea_rows, int frames, int P, int T, int k,
                                                           int n_vis) {
+  pdl_grid_sync();
   extern __shared__ float s_scores[];  // [warps][P] scores, then ranks as int
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(128) mask_select_kernel(const float* __restric
 __global__ void __launch_bounds__(256) gather_rows_kernel(const uint4* __restrict__ in, const int* __restrict__ idx,
                                                           uint4* __restrict__ out, long n_rows, int chunks_per_row,
                                                           int rows_per_group, long group_stride) {
+  pdl_grid_sync();
   const long total = n_rows * chunks_per_row;
   for (long id = (long)blockIdx.x * blockDim.x + threadIdx.x; id < total; id += (long)gridDim.x * blockDim.x) {
     const long r = id / chunks_per_row;
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint4* __restric
 constexpr int CS_ROWS = 128;
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ x, int64_t ld, float* __restrict__ out,
                                                           int M, int N) {
+  pdl_grid_sync();
   __shared__ float s_part[8][256];
   const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
@@ -164,6 +168,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
 __global__ void __launch_bounds__(256) cast_scale_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ out,
                                                               const float* __restrict__ row_scale, int rows_per_scale,
                                                               long n4, int d4) {
+  pdl_grid_sync();
   for (long id = (long)blockIdx.x * blockDim.x + threadIdx.x; id < n4; id += (long)gridDim.x * blockDim.x) {
     float4 v = x[id];
     if (row_scale) {
@@ -193,7 +198,7 @@ extern "C" int ub_patchify(const float* x, void* out, int B, int T, int H, int W
   UB_REQUIRE(H % 16 == 0 && W % 16 == 0 && H > 0 && W > 0, "patchify: H, W must be multiples of the 16-pixel patch (H=%d W=%d)", H, W);
   const long tokens = (long)B * (T / tubelet) * (H / 16) * (W / 16);
   const long runs = tokens * 3 * tubelet * 16;
-  patchify_kernel<<<flat_grid(runs, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)out, B, T, H, W, tubelet, runs);
+  UB_LAUNCH(patchify_kernel, flat_grid(runs, 256), 256, 0, (cudaStream_t)stream, x, (bf16*)out, B, T, H, W, tubelet, runs);
   return check_launch("patchify_kernel");
 }
 
@@ -205,7 +210,7 @@ extern "C" int ub_mask_select(const float* attn, const float* q, uint8_t* mask, 
   const int warps = 4;
   const size_t smem = (size_t)warps * 2 * P * sizeof(float);
   UB_REQUIRE(smem <= 48 * 1024, "mask_select: P=%d too large", P);
-  mask_select_kernel<<<(frames + warps - 1) / warps, warps * 32, smem, (cudaStream_t)stream>>>(attn, q, mask, vis_idx, tea_rows,
+  UB_LAUNCH(mask_select_kernel, (frames + warps - 1) / warps, warps * 32, smem, (cudaStream_t)stream, attn, q, mask, vis_idx, tea_rows,
                                                                                                frames, P, T, k, n_vis);
   return check_launch("mask_select_kernel");
 }
@@ -216,7 +221,7 @@ extern "C" int ub_gather_rows(const void* in, const int* idx, void* out, int64_t
   UB_REQUIRE(n_rows > 0 && row_bytes > 0 && row_bytes % 16 == 0, "gather_rows: row_bytes=%lld must be a positive multiple of 16",
              (long long)row_bytes);
   const int cpr = (int)(row_bytes / 16);
-  gather_rows_kernel<<<flat_grid(n_rows * cpr, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)in, idx, (uint4*)out, n_rows,
+  UB_LAUNCH(gather_rows_kernel, flat_grid(n_rows * cpr, 256), 256, 0, (cudaStream_t)stream, (const uint4*)in, idx, (uint4*)out, n_rows,
                                                                                     cpr, rows_per_group, group_stride_rows);
   return check_launch("gather_rows_kernel");
 }
@@ -225,7 +230,7 @@ extern "C" int ub_colsum_bf16(const void* x, int64_t ld, float* out, int M, int 
   UB_REQUIRE(x && out && M > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "colsum_bf16: N and ld must be multiples of 8 (M=%d N=%d)", M, N);
   UB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "colsum_bf16: x must be 16-byte aligned");
   dim3 grid((N + 255) / 256, (M + CS_ROWS - 1) / CS_ROWS);
-  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld, out, M, N);
+  UB_LAUNCH(colsum_bf16_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16*)x, ld, out, M, N);
   return check_launch("colsum_bf16_kernel");
 }
 
@@ -234,7 +239,7 @@ extern "C" int ub_cast_scale_bf16(const float* x, void* out, const float* row_sc
   UB_REQUIRE(x && out && rows > 0 && D > 0 && D % 4 == 0, "cast_scale_bf16: bad arguments");
   UB_REQUIRE(row_scale == nullptr || rows_per_scale > 0, "cast_scale_bf16: rows_per_scale must be > 0");
   const long n4 = rows * (D / 4);
-  cast_scale_bf16_kernel<<<flat_grid(n4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)out, row_scale,
+  UB_LAUNCH(cast_scale_bf16_kernel, flat_grid(n4, 256), 256, 0, (cudaStream_t)stream, (const float4*)x, (uint2*)out, row_scale,
                                                                               rows_per_scale, n4, D / 4);
   return check_launch("cast_scale_bf16_kernel");
 }
