@@ -115,6 +115,10 @@ UB_API int ub_l2norm_rows(float* x, int rows, int D, void* stream);
  *   ub_cast_scale_bf16  out = bf16(x * row_scale[row / rows_per_scale]).
  * ---------------------------------------------------------------------------------------------- */
 UB_API int ub_patchify(const float* x, void* out, int B, int T, int H, int W, int tubelet, void* stream);
+/* decoded uint8 frames [B,T,H,W,3] -> the same rows, with ToTensor + tensor_normalize(mean, std) applied on the way
+ * (src/datasets/kinetics_sparse.py:236-243, 434-451); mean3 / std3 are HOST pointers to 3 floats.                     */
+UB_API int ub_patchify_u8(const uint8_t* x, void* out, const float* mean3, const float* std3, int B, int T, int H, int W,
+                          int tubelet, void* stream);
 UB_API int ub_mask_select(const float* attn, const float* q, uint8_t* mask, int* vis_idx, int* tea_rows, int frames,
                           int P, int T, int k, int n_vis, void* stream);
 UB_API int ub_gather_rows(const void* in, const int* idx, void* out, int64_t n_rows, int64_t row_bytes,

@@ -87,6 +87,17 @@ def sinusoid_table(n_position: int, d_hid: int) -> Tensor:
     return torch.tensor(tab, dtype=torch.float).unsqueeze(0)
 
 
+def normalize_frames_u8(frames: Tensor, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)) -> Tensor:
+    """Decoded frames uint8 [B,T,H,W,3] -> the normalised fp32 clip [B,3,T,H,W] the models consume.
+    Follows src/datasets/kinetics_sparse.py:236-247 per clip: ToTensor (uint8 -> float / 255, :236) ... tensor_normalize
+    (:241-243, body :434-451: `tensor - mean`, then `tensor / std`, fp32) ... permute T H W C -> C T H W (:245)."""
+    assert frames.dtype == torch.uint8 and frames.shape[-1] == 3
+    t = frames.float() / 255.0
+    t = t - torch.tensor(mean, dtype=torch.float32)
+    t = t / torch.tensor(std, dtype=torch.float32)
+    return t.permute(0, 4, 1, 2, 3).contiguous()
+
+
 def patchify(x: Tensor, tubelet: int, patch: int) -> Tensor:
     """Conv3d with stride == kernel (clip.py:123-128,146; modeling_finetune.py:165-174) as an im2col.
 

@@ -57,3 +57,22 @@ def test_gemm_all_operand_majors_and_epilogues():
     ok &= g.run(256, 256, 256, a_mn=1, b_mn=1, out_fp32=1)      # wgrad form
     ok &= g.run(768, 768, 4096, a_mn=1, b_mn=1, out_fp32=1, split_k=4, accumulate=1)
     assert ok
+
+
+@pytest.mark.parametrize("tub", [1, 2])
+def test_uint8_frames_to_normalised_patches_bit_exact(tub):
+    """decoded uint8 frames [B,T,H,W,3] -> ToTensor + tensor_normalize + THWC->CTHW + patchify in one
+    kernel, bit-exact against the CPU restatement of src/datasets/kinetics_sparse.py:236-247,434-451."""
+    import torch
+    from oracle import unite_oracle as orc
+    from unite_b200 import ops
+    B, T, H, W = 2, 4, 64, 96
+    fr = torch.randint(0, 256, (B, T, H, W, 3), generator=torch.Generator().manual_seed(3 + tub), dtype=torch.uint8)
+    fr[0, 0, 0, :4] = torch.tensor([[0, 0, 0], [255, 255, 255], [1, 128, 254], [127, 0, 255]], dtype=torch.uint8)   # extremes
+    n_tok = B * (T // tub) * (H // 16) * (W // 16)
+    out = torch.empty(n_tok, 3 * tub * 256, device="cuda", dtype=torch.bfloat16)
+    ops.patchify_u8(fr.cuda(), out, tub)
+    ref = orc.patchify(orc.normalize_frames_u8(fr), tub, 16).reshape(n_tok, -1).bfloat16()
+    assert torch.equal(out.cpu(), ref)
+    with pytest.raises(Exception):
+        ops.patchify_u8(fr.cuda()[..., :2], out, tub)          # not [.., 3]

@@ -166,3 +166,28 @@ def test_vitl_student_tubelet2_teacher_kernel2_against_oracle():
     assert ref["vis_idx"].shape == (1, 320)
     eng = Stage1Engine(student.cuda().train(), teacher.cuda().eval(), mask_ratio=0.8)
     _check_step(eng, ref, videos, q, big_grad_only=True)
+
+
+def test_stage1_step_from_uint8_frames_equals_step_from_normalised_clip():
+    """§8 row f2: feeding decoded uint8 frames (normalised on the device inside the patchify kernel) gives the same mask and
+    the same loss, bit for bit, as feeding the fp32 clip the reference's data pipeline would have produced on the host."""
+    from oracle.unite_oracle import normalize_frames_u8
+    from unite_b200.engine import Stage1Engine
+    fix = load_golden("tiny_stage12.pt")
+    scfg, tcfg = oracle_cfgs(fix)
+    ssd, tsd, _ = seeded_states(fix)
+    student, teacher = _models(scfg, tcfg, ssd, tsd)
+    eng = Stage1Engine(student, teacher, mask_ratio=fix["cfg"]["mask_ratio"])
+    B, _, T, H, W = fix["videos"].shape
+    frames = torch.randint(0, 256, (B, T, H, W, 3), generator=torch.Generator().manual_seed(11), dtype=torch.uint8)
+    q = fix["q"].cuda()
+    eng.optimizer.zero_grad()
+    l_u8 = eng.forward_backward(frames.cuda(), q).clone()
+    mask_u8 = eng.last["mask"].clone()
+    g_u8 = eng.core.arena.grads.clone()
+    eng.optimizer.zero_grad()
+    l_f32 = eng.forward_backward(normalize_frames_u8(frames).cuda(), q).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(mask_u8, eng.last["mask"])
+    assert torch.equal(l_u8, l_f32), (l_u8.item(), l_f32.item())
+    assert rel_l2(g_u8, eng.core.arena.grads) < 1e-5      # fp32 red.add ordering only

@@ -124,3 +124,35 @@ def test_tiny_stage3_against_oracle():
     # decoders get no gradient in stage 3 (DDP find_unused_parameters=True in the reference, run_stage3.py:1246)
     assert float(arena.g32("clip_decoder.0.head.weight").abs().max()) == 0.0
     print(f"stage-3 loss {loss.item():.5f} vs {ref['loss'].item():.5f}; selected {int(ref['sel_mask'].sum())}/{Bt}")
+
+
+def test_evaluation_path_inference_scores_and_merge(tmp_path):
+    """all-token inference (no activations kept), validation metrics, per-view score file and merge."""
+    from oracle import unite_oracle as O
+    from unite_b200.engine_for_finetuning import final_test, merge, validation_one_epoch
+    fix = load_golden("tiny_stage12.pt")
+    scfg, _ = oracle_cfgs(fix)
+    _, _, vsd = seeded_states(fix)
+    vit = _build_vit(scfg)
+    vit.load_state_dict(vsd, strict=True)
+    vit = vit.cuda().eval()
+    g = torch.Generator().manual_seed(4)
+    clips = [torch.randn(2, 3, scfg.num_frames, scfg.img_size, scfg.img_size, generator=g) for _ in range(3)]
+    labels = [torch.randint(0, scfg.num_classes, (2,), generator=g) for _ in range(3)]
+    ref_logits = torch.cat([O.vit_forward(vsd, c, scfg) for c in clips])
+    with torch.no_grad():
+        got = torch.cat([vit(c.cuda()) for c in clips]).cpu()
+    assert rel_l2(got, ref_logits) < 1e-2
+    stats, ece = validation_one_epoch(list(zip(clips, labels)), vit, "cuda")
+    y = torch.cat(labels)
+    ref_loss = torch.nn.functional.cross_entropy(ref_logits, y).item()
+    assert abs(stats["loss"] - ref_loss) / ref_loss < 5e-3
+    assert 0.0 <= ece <= 1.0 and 0.0 <= stats["acc1"] <= stats["acc5"] <= 100.0
+    # two "views" (chunk 0 / 1) of every clip, written by two ranks' files, merged by video id
+    for rank in range(2):
+        batches = [(c, l, [f"vid{2 * i + j}" for j in range(2)], torch.full((2,), rank), torch.zeros(2)) for i, (c, l) in enumerate(zip(clips, labels))]
+        final_test(batches, vit, "cuda", str(tmp_path / f"{rank}.txt"))
+    top1, top5 = merge(str(tmp_path), 2)
+    probs = torch.softmax(got.double(), 1)                    # both views are the same clip here -> merged score == single view
+    ref_top1 = (probs.argmax(1) == y).double().mean().item() * 100
+    assert abs(top1 - ref_top1) < 1e-9 and top5 >= top1

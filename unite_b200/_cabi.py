@@ -56,6 +56,7 @@ SIGNATURES = {
     "ub_dec_tail_bwd": (C.c_int, [_P, _P, _P, _F, _P, _F, _P, _P, _P, _I, _I, _P]),
     "ub_l2norm_rows": (C.c_int, [_P, _I, _I, _P]),
     "ub_patchify": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "ub_patchify_u8": (C.c_int, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _I, _I, _I, _I, _P]),
     "ub_mask_select": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ub_gather_rows": (C.c_int, [_P, _P, _P, _L, _L, _I, _L, _P]),
     "ub_colsum_bf16": (C.c_int, [_P, _L, _P, _I, _I, _P]),

@@ -114,7 +114,18 @@ class Stage1Engine:
         core, teacher = self.core, self.teacher
         B = videos.shape[0]
         patches = None
-        if self.share_patches:
+        patches_s = None
+        if videos.dtype == U8:
+            # decoded frames uint8 [B,T,H,W,3]: normalise + patchify in one pass; the fp32 clip the
+            # reference materialises never exists — `videos` below is a zero-stride shape carrier
+            _, T_, H_, W_, _c = videos.shape
+            ks, tub = teacher.kernel_size, self.student.encoder.patch_embed.tubelet_size
+            n_tok = lambda k: B * (T_ // k) * (H_ // 16) * (W_ // 16)
+            patches = ops.patchify_u8(videos, torch.empty(n_tok(ks), 3 * ks * 256, device=videos.device, dtype=BF16), ks)
+            patches_s = patches if self.share_patches else ops.patchify_u8(
+                videos, torch.empty(n_tok(tub), 3 * tub * 256, device=videos.device, dtype=BF16), tub)
+            videos = torch.empty(1, device=videos.device, dtype=F32).expand(B, 3, T_, H_, W_)
+        elif self.share_patches:
             ks = teacher.kernel_size
             n_tok = B * (videos.shape[2] // ks) * (videos.shape[3] // 16) * (videos.shape[4] // 16)
             patches = torch.empty(n_tok, 3 * ks * 256, device=videos.device, dtype=BF16)
@@ -143,7 +154,9 @@ class Stage1Engine:
         if dp is None and self.student.training:
             dp = drop_path_factors(self.student.encoder.drop_path_rates, B, videos.device)
         self.loss.zero_()
-        _, x_clip, state = core.run_forward(videos, vis_idx[0], patches if self.share_patches else None, dp, True, True,
+        if patches_s is None:
+            patches_s = patches if self.share_patches else None
+        _, x_clip, state = core.run_forward(videos, vis_idx[0], patches_s, dp, True, True,
                                             targets=targets, loss_acc=self.loss)
         core.run_backward(state, targets=targets, grad_sync=self.grad_sync)
         self.last = dict(attn=attn, mask=mask.view(B, Tp * P).bool(), vis_idx=vis_idx[0], targets=targets, outputs=x_clip)

@@ -91,3 +91,139 @@ def train_one_epoch(model: torch.nn.Module, criterion=None, data_loader: Iterabl
     lrs = [g["lr"] for g in optimizer.param_groups]
     return {"loss": loss_avg, "class_acc": (correct / max(seen, 1)).item(), "loss_scale": 1.0, "lr": max(lrs), "min_lr": min(lrs),
             "grad_norm": optimizer.grad_norm().item()}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Evaluation path: all-token inference + multi-crop / multi-segment score merge
+# (src/engines/engine_for_finetuning.py:175-351).  The forward is the inference form of the same kernels (S = all
+# tokens, no activations kept); metrics stay on the device until the end of the loop (one sync per loader, not per batch).
+# ---------------------------------------------------------------------------------------------------------------------
+def accuracy(output: torch.Tensor, target: torch.Tensor, topk=(1,)):
+    """timm.utils.accuracy (timm 0.4.12, pinned by environment.yaml; the package is not under /root/reference): top-k
+    precision in percent over the batch."""
+    maxk = min(max(topk), output.shape[1])
+    pred = output.topk(maxk, 1, True, True).indices.t()
+    correct = pred.eq(target.reshape(1, -1).expand_as(pred))
+    return [correct[:min(k, maxk)].reshape(-1).float().sum(0) * 100.0 / target.shape[0] for k in topk]
+
+
+def compute_ece(softmaxes: torch.Tensor, labels: torch.Tensor, n_bins: int = 15) -> float:
+    """Expected calibration error.  The reference imports it from src/knn.py, which is missing from the tree (SURVEY.md
+    §0.1): this is the standard equal-width 15-bin estimator sum_b |acc_b - conf_b| * n_b / n."""
+    conf, pred = softmaxes.max(dim=1)
+    acc = pred.eq(labels).float()
+    edges = torch.linspace(0, 1, n_bins + 1, device=softmaxes.device)
+    ece = torch.zeros((), device=softmaxes.device)
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        m = (conf > lo) & (conf <= hi)
+        n = m.float().sum()
+        if n > 0:
+            ece = ece + (acc[m].mean() - conf[m].mean()).abs() * n / conf.numel()
+    return float(ece)
+
+
+def _gather_all(t: torch.Tensor) -> torch.Tensor:
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return t
+    parts = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, t.contiguous())
+    return torch.cat(parts)
+
+
+@torch.no_grad()
+def validation_one_epoch(data_loader, model, device, save_preds_path=None):
+    """engine_for_finetuning.py:175-236: returns ({loss, acc1, acc5}, ece)."""
+    model.eval()
+    net = model.module if hasattr(model, "module") else model
+    dev = net.core().arena.device
+    probs, labels, losses = [], [], []
+    for batch in data_loader:
+        videos, target = batch[0].to(dev, non_blocking=True), batch[1].to(dev, non_blocking=True)
+        output = model(videos)
+        losses.append(torch.nn.functional.cross_entropy(output, target.long(), reduction="sum"))
+        probs.append(torch.softmax(output, dim=1))
+        labels.append(target.long())
+    probs, labels = _gather_all(torch.cat(probs)), _gather_all(torch.cat(labels))
+    loss = _gather_all(torch.stack(losses).sum().reshape(1)).sum() / labels.numel()
+    acc1, acc5 = accuracy(probs, labels, topk=(1, 5))
+    ece = compute_ece(probs, labels)
+    print(f"Expected Calibration Error (ECE): {ece:.4f}")
+    if save_preds_path is not None:
+        import os
+        import numpy as np
+        os.makedirs(save_preds_path, exist_ok=True)
+        np.save(os.path.join(save_preds_path, "preds.npy"), probs.argmax(1).cpu().numpy())
+        np.save(os.path.join(save_preds_path, "labels.npy"), labels.cpu().numpy())
+    stats = {"loss": loss.item(), "acc1": acc1.item(), "acc5": acc5.item()}
+    print("* Acc@1 {acc1:.3f} Acc@5 {acc5:.3f} loss {loss:.3f}".format(**stats))
+    return stats, ece
+
+
+@torch.no_grad()
+def final_test(data_loader, model, device, file):
+    """engine_for_finetuning.py:241-296: per-view logits written as `<id> <logits list> <label> <chunk> <split>` lines (the
+    format `merge` parses), first line `<acc1>, <acc5>` of the last batch like the reference.  batch = (videos, target,
+    ids, chunk_nb, split_nb)."""
+    model.eval()
+    net = model.module if hasattr(model, "module") else model
+    dev = net.core().arena.device
+    lines, probs, labels, losses = [], [], [], []
+    acc1 = acc5 = torch.zeros(())
+    for batch in data_loader:
+        videos, target, ids, chunk_nb, split_nb = batch[0], batch[1], batch[2], batch[3], batch[4]
+        videos, target = videos.to(dev, non_blocking=True), target.to(dev, non_blocking=True)
+        output = model(videos)
+        losses.append(torch.nn.functional.cross_entropy(output, target.long(), reduction="sum"))
+        out_host, tgt_host = output.float().cpu(), target.cpu()
+        for i in range(out_host.shape[0]):
+            lines.append("{} {} {} {} {}\n".format(ids[i], str(out_host[i].numpy().tolist()), str(int(tgt_host[i])),
+                                                   str(int(chunk_nb[i])), str(int(split_nb[i]))))
+        acc1, acc5 = accuracy(output, target.long(), topk=(1, 5))
+        probs.append(torch.softmax(output, dim=1))
+        labels.append(target.long())
+    probs, labels = torch.cat(probs), torch.cat(labels)
+    ece = compute_ece(probs, labels)
+    print(f"Expected Calibration Error (ECE): {ece:.4f}")
+    with open(file, "w") as f:
+        f.write("{}, {}\n".format(acc1, acc5))
+        f.writelines(lines)
+    a1, a5 = accuracy(probs, labels, topk=(1, 5))
+    stats = {"loss": (torch.stack(losses).sum() / labels.numel()).item(), "acc1": a1.item(), "acc5": a5.item()}
+    print("* Acc@1 {acc1:.3f} Acc@5 {acc5:.3f} loss {loss:.3f}".format(**stats))
+    return stats, ece
+
+
+def compute_video(item):
+    """engine_for_finetuning.py:343-351: mean of the per-view softmax scores of one video -> (pred, top1, top5, label)."""
+    import numpy as np
+    _, _, data, label = item
+    feat = np.mean(np.stack(data), axis=0)
+    pred = int(np.argmax(feat))
+    return [pred, float(pred == int(label)), float(int(label) in np.argsort(-feat)[:5]), int(label)]
+
+
+def merge(eval_path, num_tasks):
+    """engine_for_finetuning.py:299-341: read the per-rank `<rank>.txt` files of final_test, softmax each view, drop repeated
+    (chunk, split) views of a video, average the rest, return (top-1 %, top-5 %)."""
+    import os
+    import numpy as np
+    feats, label_of, seen = {}, {}, {}
+    for r in range(num_tasks):
+        with open(os.path.join(eval_path, str(r) + ".txt")) as f:
+            rows = f.readlines()[1:]
+        for line in rows:
+            line = line.strip()
+            name, rest = line.rsplit("[", maxsplit=1)
+            vec, tail = rest.rsplit("]", maxsplit=1)
+            _, label, chunk_nb, split_nb = tail.split(" ")[:4]
+            x = np.array([float(t) for t in vec.split(",")], dtype=np.float64)
+            e = np.exp(x - x.max())
+            view = chunk_nb + split_nb
+            if view in seen.setdefault(name, []):
+                continue
+            seen[name].append(view)
+            feats.setdefault(name, []).append(e / e.sum())
+            label_of[name] = label
+    ans = [compute_video([i, n, feats[n], label_of[n]]) for i, n in enumerate(feats)]
+    return float(np.mean([a[1] for a in ans])) * 100, float(np.mean([a[2] for a in ans])) * 100

@@ -178,6 +178,20 @@ def patchify(x, out, tubelet):
     return out
 
 
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)      # kinetics_sparse.py:241-243
+
+
+@_instrument("patchify", 1)
+def patchify_u8(x, out, tubelet, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """x uint8 [B,T,H,W,3] (decoder layout) -> normalised bf16 im2col rows (ToTensor + tensor_normalize + permute + patchify)."""
+    if x.dim() != 5 or x.shape[-1] != 3 or not x.is_contiguous():
+        raise _cabi.UBError(f"patchify_u8: contiguous uint8 [B,T,H,W,3] expected, got {tuple(x.shape)}")
+    B, T, H, W, _ = x.shape
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    check(lib.ub_patchify_u8(_p(x, U8, "frames"), _p(out, BF16, "patches"), m3, s3, B, T, H, W, tubelet, _stream()), "ub_patchify_u8")
+    return out
+
+
 @_instrument("mask_select", 1)
 def mask_select(attn, q, mask, vis_idx, tea_rows, T, k, n_vis):
     frames, P = attn.shape

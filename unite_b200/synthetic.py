@@ -13,14 +13,19 @@ import torch
 
 class SyntheticStage1Loader:
     def __init__(self, batch_size, num_frames=8, img_size=224, steps=10, seed=0, rank=0, n_distinct=2, num_classes=12,
-                 frames_per_token=1, pin=True):
+                 frames_per_token=1, pin=True, uint8=False):
+        """uint8=True: batches carry DECODED frames uint8 [B,T,H,W,3] (what decord / NVDEC hand over, kinetics_sparse.py:
+        loadvideo_decord) instead of the normalised fp32 clip; the engine normalises on the device (ops.patchify_u8)."""
         g = torch.Generator().manual_seed(seed + rank)
         self.steps = steps
         self.batches = []
         pin = pin and torch.cuda.is_available()
         HW = (img_size // 16) ** 2
         for _ in range(n_distinct):
-            v = torch.randn(batch_size, 3, num_frames, img_size, img_size, generator=g)
+            if uint8:
+                v = torch.randint(0, 256, (batch_size, num_frames, img_size, img_size, 3), generator=g, dtype=torch.uint8)
+            else:
+                v = torch.randn(batch_size, 3, num_frames, img_size, img_size, generator=g)
             q = torch.empty(batch_size * (num_frames // frames_per_token), HW).exponential_(1, generator=g)
             y = torch.randint(0, num_classes, (batch_size,), generator=g)
             if pin:
