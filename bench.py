@@ -247,6 +247,28 @@ def main():
     h2d = B * 3 * 8 * 224 * 224 * 4 + B * 8 * 196 * 4
     d2h = 4
 
+    # ---- the same, fed with DECODED uint8 frames [B,T,H,W,3] (what decord / NVDEC deliver; normalised inside the patchify
+    #      kernel): 4x fewer H2D bytes per step.  Reported beside e2e, not instead of it.
+    e2e_u8 = None
+    if os.environ.get("UB_BENCH_U8", "1") != "0":
+        loader8 = SyntheticStage1Loader(B, steps=args.steps, seed=0, rank=rank, n_distinct=2, uint8=True)
+        warm8 = SyntheticStage1Loader(B, steps=3, seed=0, rank=rank, n_distinct=1, uint8=True)
+        train_one_epoch(model, warm8, None, eng.optimizer, dev, 0, None, teacher_model=teacher, mask_type="attention", mask_ratio=0.8,
+                        args=_Args)
+        sync_all()
+        e0.record()
+        train_one_epoch(model, loader8, None, eng.optimizer, dev, 0, None, teacher_model=teacher, mask_type="attention", mask_ratio=0.8,
+                        args=_Args)
+        e1.record()
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        u8_ms = t.item() / args.steps
+        e2e_u8 = dict(value=round(world * B / (u8_ms * 1e-3), 2), unit="clips/s", ms_per_step=round(u8_ms, 3),
+                      h2d_bytes_per_step=B * 8 * 224 * 224 * 3 + B * 8 * 196 * 4, d2h_bytes_per_step=4,
+                      input="uint8 frames [B,T,H,W,3], ImageNet-normalised on the device inside the patchify kernel")
+
     # ---- one instrumented step: per-op CUDA-event durations on the launching stream (roofline of the GEMM kernel) --
     roof, breakdown = None, None
     if rank == 0:
@@ -329,7 +351,7 @@ def main():
         clocks=clocks,
         e2e=dict(value=round(e2e_value, 2), unit="clips/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=round(e2e_ms, 3),
                  api="unite_b200.engine_for_pretraining.train_one_epoch (reference run_stage1.py:294 signature), pinned host batches"),
-        gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
+        e2e_uint8_frames=e2e_u8, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
         mfu=dict(alg_gflop_per_clip=F_ALG_GFLOP_PER_CLIP, tflops_per_gpu=round(per_gpu * F_ALG_GFLOP_PER_CLIP / 1e3, 1),
                  of_nominal_2250=round(per_gpu * F_ALG_GFLOP_PER_CLIP / 1e3 / NOMINAL_BF16_TFLOPS, 4),
                  of_measured_sustained=round(per_gpu * F_ALG_GFLOP_PER_CLIP / 1e3 / measured_peaks()["bf16"], 4)),

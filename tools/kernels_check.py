@@ -40,7 +40,9 @@ def check_attention(n_seq, S, H, time_it=False):
     p = s.softmax(-1)
     oref = (p @ v)
     report(f"attn_fwd o   S={S} H={H}", o.view(n_seq, S, H, 64).permute(0, 2, 1, 3), oref, 6e-3)
-    report(f"attn_fwd lse S={S} H={H}", lse, torch.logsumexp(s, -1), 1e-4)
+    # the tcgen05 forward sums the bf16 P it multiplies with V (row sum on the tensor core): |d lse| <= 2^-9, so O stays
+    # exactly normalised w.r.t. the P the backward recomputes from this lse
+    report(f"attn_fwd lse S={S} H={H}", lse, torch.logsumexp(s, -1), 5e-4)
     d_o = (torch.randn(n_seq * S, H * 64, device=dev, generator=g)).bfloat16()
     oref.backward(d_o.float().view(n_seq, S, H, 64).permute(0, 2, 1, 3))
     dqkv = torch.zeros_like(qkv)

@@ -547,6 +547,7 @@ __global__ void cls_attn_kernel(const bf16* __restrict__ qkv, float* __restrict_
 
 namespace ub {
 int launch_attn_fwd_tc(const void* qkv, void* o, int n_seq, int S, int H, float scale, cudaStream_t stream);
+int launch_attn_fwd_lse_tc(const void* qkv, void* o, float* lse, int n_seq, int S, int H, float scale, cudaStream_t stream);
 int launch_attn_bwd_tc(const void* qkv, const void* d_o, const float* lse, const float* Dv, void* dqkv, int n_seq, int S, int H,
                        float scale, cudaStream_t stream);
 }
@@ -564,6 +565,13 @@ extern "C" int ub_attn_fwd(const void* qkv, void* o, float* lse, int n_seq, int 
   }
   if (use_tc && lse == nullptr && S <= 240) return   // (K and V for NK <= 240 padded keys fit the 227 KB smem budget twice)
     launch_attn_fwd_tc(qkv, o, n_seq, S, H, scale, (cudaStream_t)stream);
+  // training forward (LSE kept for the backward) over the student's <= 320 visible tokens: two-chunk tcgen05 kernel
+  static int use_tc_lse = -1;
+  if (use_tc_lse < 0) {
+    const char* e = getenv("UB_ATTN_FWD_LSE_TC");
+    use_tc_lse = e ? atoi(e) : 1;
+  }
+  if (use_tc_lse && lse != nullptr && S <= 320) return launch_attn_fwd_lse_tc(qkv, o, lse, n_seq, S, H, scale, (cudaStream_t)stream);
   dim3 grid((S + TQ - 1) / TQ, H, n_seq);
   UB_LAUNCH(attn_fwd_kernel, grid, 128, 0, (cudaStream_t)stream, (const bf16*)qkv, (bf16*)o, lse, S, H, scale);
   return check_launch("attn_fwd_kernel");

@@ -167,9 +167,8 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint4* __restric
 // 256 columns x ROWS_PER_CTA rows with 4 independent loads in flight per thread, then reduces the 8 row-groups
 // through smem and issues one red.add per column.
 // ------------------------------------------------------------------------------------------------
-constexpr int CS_ROWS = 128;
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ x, int64_t ld, float* __restrict__ out,
-                                                          int M, int N) {
+                                                          int M, int N, int CS_ROWS) {
   pdl_grid_sync();
   __shared__ float s_part[8][256];
   const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
@@ -285,8 +284,14 @@ extern "C" int ub_gather_rows(const void* in, const int* idx, void* out, int64_t
 extern "C" int ub_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, void* stream) {
   UB_REQUIRE(x && out && M > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "colsum_bf16: N and ld must be multiples of 8 (M=%d N=%d)", M, N);
   UB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "colsum_bf16: x must be 16-byte aligned");
-  dim3 grid((N + 255) / 256, (M + CS_ROWS - 1) / CS_ROWS);
-  UB_LAUNCH(colsum_bf16_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16*)x, ld, out, M, N);
+  // rows per CTA (multiple of 32): small enough that the grid keeps ~6 CTAs per SM in flight — this is a latency-bound pass
+  // over a few tens of MB, so bytes in flight per SM matter more than the number of atomics at the end
+  const int gx = (N + 255) / 256;
+  const int want_y = (6 * sm_count() + gx - 1) / gx;
+  int rows = ((M + want_y - 1) / want_y + 31) / 32 * 32;
+  rows = rows < 32 ? 32 : (rows > 128 ? 128 : rows);
+  dim3 grid(gx, (M + rows - 1) / rows);
+  UB_LAUNCH(colsum_bf16_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16*)x, ld, out, M, N, rows);
   return check_launch("colsum_bf16_kernel");
 }
 

@@ -103,8 +103,10 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
         torch.cuda.current_stream(dev).wait_event(ev)
         videos.record_stream(torch.cuda.current_stream(dev))
         if noise is None:
-            frames = videos.shape[0] * (videos.shape[2] // eng.teacher.kernel_size)
-            noise = torch.empty(frames, (videos.shape[3] // 16) * (videos.shape[4] // 16), device=dev).exponential_(1)
+            # fp32 clips are [B,3,T,H,W]; decoded uint8 frames are [B,T,H,W,3]
+            T_, H_, W_ = (videos.shape[1:4] if videos.dtype == torch.uint8 else videos.shape[2:5])
+            frames = videos.shape[0] * (T_ // eng.teacher.kernel_size)
+            noise = torch.empty(frames, (H_ // 16) * (W_ // 16), device=dev).exponential_(1)
         else:
             noise.record_stream(torch.cuda.current_stream(dev))
         staged = fetch(nxt) if nxt is not None else None                       # overlaps with this step's compute
