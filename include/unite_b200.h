@@ -135,9 +135,10 @@ UB_API int ub_adamw(float* p, const float* g, float* m, float* v, void* w_bf16 /
                     int64_t n_decay, float lr, float wd, float beta1, float beta2, float eps, int step, float grad_scale,
                     void* stream);
 /* same update, per-step scalars in device memory: hyper[8] = lr, wd, beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t), grad_scale
- * (lets the launch sit in a CUDA graph replayed every step) */
+ * (lets the launch sit in a CUDA graph replayed every step).  gnorm_sq (may be NULL): += sum g^2 of the raw gradients read
+ * by this very pass — the global gradient norm of utils.py:631-643 without a second sweep over the arena. */
 UB_API int ub_adamw_dev(float* p, const float* g, float* m, float* v, void* w_bf16 /* may be NULL */, int64_t n,
-                        int64_t n_decay, const float* hyper, void* stream);
+                        int64_t n_decay, const float* hyper, float* gnorm_sq /* may be NULL */, void* stream);
 UB_API int ub_cast_bf16(const float* x, void* out, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

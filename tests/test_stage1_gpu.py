@@ -145,6 +145,22 @@ def test_optimizer_step_matches_torch_adamw():
     for k, p in ps.items():
         assert rel_l2(student.state_dict()[k], p) < 1e-6, k
     assert abs(eng.optimizer.grad_norm().item() - torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).item()) < 1e-3
+    # graph-friendly form (scalars in device memory, gradient norm accumulated by the AdamW pass itself): same update
+    eng.optimizer.zero_grad()
+    eng.forward_backward(videos, q)
+    g2 = eng.core.arena.grads.clone()
+    p_before = eng.core.arena.params.clone()
+    m_before, v_before = eng.optimizer.exp_avg.clone(), eng.optimizer.exp_avg_sq.clone()
+    eng.optimizer.prepare_step()
+    eng.optimizer.step_dev()
+    torch.cuda.synchronize()
+    p_dev = eng.core.arena.params.clone()
+    assert abs(eng.optimizer.grad_norm().item() - g2.double().norm().item()) < 1e-3 * g2.double().norm().item() + 1e-6
+    eng.core.arena.params.copy_(p_before); eng.optimizer.exp_avg.copy_(m_before); eng.optimizer.exp_avg_sq.copy_(v_before)
+    eng.optimizer.step_count -= 1
+    eng.optimizer.step()
+    torch.cuda.synchronize()
+    assert rel_l2(p_dev, eng.core.arena.params) < 1e-6
 
 
 def test_vitl_student_tubelet2_teacher_kernel2_against_oracle():

@@ -63,7 +63,7 @@ SIGNATURES = {
     "ub_cast_scale_bf16": (C.c_int, [_P, _P, _P, _I, _L, _I, _P]),
     "ub_sumsq": (C.c_int, [_P, _L, _P, _P]),
     "ub_adamw": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
-    "ub_adamw_dev": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _P, _P]),
+    "ub_adamw_dev": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P]),
     "ub_cast_bf16": (C.c_int, [_P, _P, _L, _P]),
     "ub_meanpool_fwd": (C.c_int, [_P, _P, _I, _I, _I, _P]),
     "ub_meanpool_bwd": (C.c_int, [_P, _P, _I, _I, _I, _P]),

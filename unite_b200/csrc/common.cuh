@@ -125,6 +125,35 @@ UB_DEVINL float gelu_erf_grad(float x) {
   return fmaf(0.5f * x * sech2, dudx, fmaf(0.5f, t, 0.5f));
 }
 #endif
+// Two elements at a time on the packed fp32x2 pipe (FMUL2 / FFMA2): the K = 768 GELU epilogues are bound by FP32 issue
+// slots, and the packed forms halve every instruction except the two MUFU.TANH.
+#ifndef UB_GELU_ERF
+UB_DEVINL float2 gelu_erf2(float2 x) {
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 in = __ffma2_rn(x2, make_float2(0.0356774081f, 0.0356774081f), make_float2(0.7978845608f, 0.7978845608f));
+  const float2 u = __fmul2_rn(x, in);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, t, hx);
+}
+UB_DEVINL float2 gelu_erf_grad2(float2 x) {
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 in = __ffma2_rn(x2, make_float2(0.0356774081f, 0.0356774081f), make_float2(0.7978845608f, 0.7978845608f));
+  const float2 u = __fmul2_rn(x, in);
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  const float2 dudx = __ffma2_rn(x2, make_float2(0.1070322243f, 0.1070322243f), make_float2(0.7978845608f, 0.7978845608f));
+  const float2 sech2 = __ffma2_rn(make_float2(-t.x, -t.y), t, make_float2(1.0f, 1.0f));
+  const float2 hxs = __fmul2_rn(__fmul2_rn(x, make_float2(0.5f, 0.5f)), sech2);
+  return __ffma2_rn(hxs, dudx, __ffma2_rn(t, make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f)));
+}
+#else
+UB_DEVINL float2 gelu_erf2(float2 x) { return make_float2(gelu_erf(x.x), gelu_erf(x.y)); }
+UB_DEVINL float2 gelu_erf_grad2(float2 x) { return make_float2(gelu_erf_grad(x.x), gelu_erf_grad(x.y)); }
+#endif
 // QuickGELU (teacher, clip.py:29): x * sigmoid(1.702 x) = 0.5x * (1 + tanh(0.851 x)); one MUFU op
 UB_DEVINL float quick_gelu(float x) {
   float t;

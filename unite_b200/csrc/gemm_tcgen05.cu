@@ -321,7 +321,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
               }
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+              for (int i = 0; i < 32; i += 2) {
+                const float2 y = gelu_erf2(make_float2(v[i], v[i + 1]));
+                v[i] = y.x; v[i + 1] = y.y;
+              }
             }
           }
           if (EPI == 2) {
@@ -332,11 +335,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                            : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w)
                            : "r"(slab0_a + ((uint32_t)b << 12) + rowoff + ((((uint32_t)(h * 4 + j)) ^ sw) << 4)));
-              const float2 a0 = unpack_bf16x2(pk.x), a1 = unpack_bf16x2(pk.y), a2 = unpack_bf16x2(pk.z), a3 = unpack_bf16x2(pk.w);
-              v[8 * j] *= gelu_erf_grad(a0.x); v[8 * j + 1] *= gelu_erf_grad(a0.y);
-              v[8 * j + 2] *= gelu_erf_grad(a1.x); v[8 * j + 3] *= gelu_erf_grad(a1.y);
-              v[8 * j + 4] *= gelu_erf_grad(a2.x); v[8 * j + 5] *= gelu_erf_grad(a2.y);
-              v[8 * j + 6] *= gelu_erf_grad(a3.x); v[8 * j + 7] *= gelu_erf_grad(a3.y);
+              const float2 g0 = gelu_erf_grad2(unpack_bf16x2(pk.x)), g1 = gelu_erf_grad2(unpack_bf16x2(pk.y));
+              const float2 g2 = gelu_erf_grad2(unpack_bf16x2(pk.z)), g3 = gelu_erf_grad2(unpack_bf16x2(pk.w));
+              v[8 * j] *= g0.x; v[8 * j + 1] *= g0.y;
+              v[8 * j + 2] *= g1.x; v[8 * j + 3] *= g1.y;
+              v[8 * j + 4] *= g2.x; v[8 * j + 5] *= g2.y;
+              v[8 * j + 6] *= g3.x; v[8 * j + 7] *= g3.y;
             }
           }
           if (p.row_scale != nullptr) {

@@ -65,13 +65,16 @@ __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, cons
 // those 32 bytes.
 __global__ void __launch_bounds__(256) adamw_dev_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
                                                         float4* __restrict__ v, uint2* __restrict__ w_bf16, long n4, long n4_decay,
-                                                        const float* __restrict__ hyper) {
+                                                        const float* __restrict__ hyper, float* __restrict__ gnorm_sq) {
   pdl_grid_sync();
+  __shared__ float s_part[8];
+  float gacc = 0.f;                    // sum of squares of the raw gradients this thread reads (utils.py:631-643 for free)
   const float lr = hyper[0], wd = hyper[1], beta1 = hyper[2], beta2 = hyper[3], eps = hyper[4], bc1 = hyper[5], bc2_sqrt = hyper[6],
               grad_scale = hyper[7];
   const float step_size = lr / bc1;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
     float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    gacc += gg.x * gg.x + gg.y * gg.y + gg.z * gg.z + gg.w * gg.w;
     const float decay = (i < n4_decay) ? (1.0f - lr * wd) : 1.0f;
 #define UB_ADAM_ONE(c)                                               \
   {                                                                  \
@@ -89,6 +92,16 @@ __global__ void __launch_bounds__(256) adamw_dev_kernel(float4* __restrict__ p, 
       o.x = pack_bf16x2(pp.x, pp.y);
       o.y = pack_bf16x2(pp.z, pp.w);
       w_bf16[i] = o;
+    }
+  }
+  if (gnorm_sq != nullptr) {
+    gacc = warp_sum(gacc);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = gacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[w];
+      atomicAdd(gnorm_sq, t);
     }
   }
 }
@@ -135,12 +148,12 @@ extern "C" int ub_adamw(float* p, const float* g, float* m, float* v, void* w_bf
 }
 
 extern "C" int ub_adamw_dev(float* p, const float* g, float* m, float* v, void* w_bf16, int64_t n, int64_t n_decay,
-                            const float* hyper, void* stream) {
+                            const float* hyper, float* gnorm_sq, void* stream) {
   UB_REQUIRE(p && g && m && v && hyper, "adamw_dev: null pointer");
   UB_REQUIRE(n > 0 && n % 4 == 0 && n_decay % 4 == 0 && n_decay >= 0 && n_decay <= n,
              "adamw_dev: n=%lld and n_decay=%lld must be multiples of 4", (long long)n, (long long)n_decay);
   UB_LAUNCH(adamw_dev_kernel, flat_grid4(n / 4), 256, 0, (cudaStream_t)stream, (float4*)p, (const float4*)g, (float4*)m, (float4*)v,
-                                                                       (uint2*)w_bf16, n / 4, n_decay / 4, hyper);
+                                                                       (uint2*)w_bf16, n / 4, n_decay / 4, hyper, gnorm_sq);
   return check_launch("adamw_dev_kernel");
 }
 

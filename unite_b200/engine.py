@@ -60,8 +60,7 @@ class FusedAdamW:
         """Device side: grad-norm + AdamW reading the scalars uploaded by prepare_step (capturable in a CUDA graph)."""
         a = self.arena
         self.gnorm_sq.zero_()
-        ops.sumsq(a.grads, self.gnorm_sq)
-        ops.adamw_dev(a.params, a.grads, self.exp_avg, self.exp_avg_sq, a.w16, a.n_decay, self._hyper_dev)
+        ops.adamw_dev(a.params, a.grads, self.exp_avg, self.exp_avg_sq, a.w16, a.n_decay, self._hyper_dev, self.gnorm_sq)
 
     def step(self, grad_scale: float = 1.0):
         a = self.arena

@@ -234,9 +234,9 @@ def adamw(p, g, m, v, w16, n_decay, lr, wd, beta1, beta2, eps, step, grad_scale=
 
 
 @_instrument("adamw", 1)
-def adamw_dev(p, g, m, v, w16, n_decay, hyper):
+def adamw_dev(p, g, m, v, w16, n_decay, hyper, gnorm_sq=None):
     check(lib.ub_adamw_dev(_p(p, F32, "p"), _p(g, F32, "g"), _p(m, F32, "m"), _p(v, F32, "v"), _p(w16, BF16, "w16"), p.numel(), n_decay,
-                           _p(hyper, F32, "hyper"), _stream()), "ub_adamw_dev")
+                           _p(hyper, F32, "hyper"), _p(gnorm_sq, F32, "gnorm_sq"), _stream()), "ub_adamw_dev")
 
 
 @_instrument("cast_bf16", 1)
