@@ -38,7 +38,9 @@ bool pdl_enabled();   // programmatic dependent launch for every kernel of the l
 // ----------------------------------------------------------------------------------------------
 UB_DEVINL void pdl_grid_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifndef UB_PDL_NO_TRIGGER
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

@@ -15,6 +15,7 @@ import torch
 from .engine import Stage1Engine
 
 _ENGINES = {}
+_IO = {}          # per device: copy stream, device staging ring, pinned loss read-back slots
 
 
 def _engine_for(model, teacher_model, mask_ratio, optimizer, use_graph=False):
@@ -54,9 +55,27 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
     # Input pipeline: the H2D copy of batch i+1 runs on a side stream while batch i computes (pinned host memory, as
     # DataLoader(pin_memory=True) + .to(device, non_blocking=True) at run_stage1.py:349 intend), and the per-step loss is
     # read back through a pinned buffer one step late, so neither direction stalls the launch queue.
-    copy_stream = torch.cuda.Stream(device=dev)
-    pin_loss = [torch.empty(1, pin_memory=True) for _ in range(2)]
+    io = _IO.setdefault(dev, dict(stream=torch.cuda.Stream(device=dev), ring={}, free={}, pos=[0],
+                                  pin_loss=[torch.empty(1, pin_memory=True) for _ in range(2)]))
+    copy_stream = io["stream"]           # persistent: the caching allocator keeps one pool per stream
+    pin_loss = io["pin_loss"]
     loss_ev = [None, None]
+    # Device staging ring (3 slots per tensor shape): allocating a fresh 154 MB tensor per step on the copy stream makes the
+    # caching allocator cudaMalloc (a device-wide sync) whenever record_stream delays a block's reuse — measured as steps of
+    # 32-92 ms between 19 ms ones.  A slot is rewritten only after the step that consumed it has been enqueued AND finished.
+    ring, ring_free, ring_pos = io["ring"], io["free"], io["pos"]
+
+    def stage(src):
+        key = (tuple(src.shape), src.dtype)
+        if key not in ring:
+            ring[key] = [torch.empty(src.shape, dtype=src.dtype, device=dev) for _ in range(3)]
+            ring_free[key] = [None, None, None]
+        k = ring_pos[0] % 3
+        if ring_free[key][k] is not None:
+            copy_stream.wait_event(ring_free[key][k])
+        dst = ring[key][k]
+        dst.copy_(src, non_blocking=True)
+        return dst, (key, k)
 
     def fetch(batch):
         videos, noise = batch[0], (batch[3] if len(batch) > 3 else None)
@@ -71,11 +90,12 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
             if noise is not None and len(tb) > 3:
                 noise = torch.cat([noise, tb[3]], dim=0)
         with torch.cuda.stream(copy_stream):
-            v = videos.to(dev, non_blocking=True)                              # run_stage1.py:349
-            q = None if noise is None else noise.to(dev, non_blocking=True)
+            v, slot_v = stage(videos)                                          # run_stage1.py:349 (.to(device, non_blocking=True))
+            q, slot_q = (None, None) if noise is None else stage(noise)
+            ring_pos[0] += 1
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return v, q, ev
+        return v, q, ev, (slot_v, slot_q)
 
     def check(slot):
         nonlocal last_loss
@@ -92,7 +112,7 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
     staged = fetch(nxt) if nxt is not None else None
     step = 0
     while staged is not None:
-        videos, noise, ev = staged
+        videos, noise, ev, slots = staged
         nxt = next(it_loader, None)
         it = start_steps + step
         for group in opt.param_groups:                                         # run_stage1.py:326-338
@@ -101,16 +121,18 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
             if wd_schedule_values is not None and group["weight_decay"] > 0:
                 group["weight_decay"] = wd_schedule_values[min(it, len(wd_schedule_values) - 1)]
         torch.cuda.current_stream(dev).wait_event(ev)
-        videos.record_stream(torch.cuda.current_stream(dev))
         if noise is None:
             # fp32 clips are [B,3,T,H,W]; decoded uint8 frames are [B,T,H,W,3]
             T_, H_, W_ = (videos.shape[1:4] if videos.dtype == torch.uint8 else videos.shape[2:5])
             frames = videos.shape[0] * (T_ // eng.teacher.kernel_size)
             noise = torch.empty(frames, (H_ // 16) * (W_ // 16), device=dev).exponential_(1)
-        else:
-            noise.record_stream(torch.cuda.current_stream(dev))
         staged = fetch(nxt) if nxt is not None else None                       # overlaps with this step's compute
         loss = eng.step(videos, noise)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(dev))
+        for sl in slots:
+            if sl is not None:
+                ring_free[sl[0]][sl[1]] = done
         loss_sum += loss
         gn_sum += opt.grad_norm(1.0 / (eng.grad_sync.world if eng.grad_sync is not None else 1))
         n += 1
