@@ -49,6 +49,8 @@ typedef struct ub_gemm_epilogue {
   int32_t act;      /* UB_ACT_*                                                                           */
   int32_t out_fp32; /* 0: C is bf16, 1: C is fp32                                                         */
   int32_t accumulate; /* 1: C (fp32) += result with red.add (required when split_k > 1)                   */
+  int32_t tile_ctas;  /* scheduling hint: 0 = cost model, 1 / 2 / 4 = CTAs per work item (4 = two pairs + B multicast) */
+  int32_t max_ctas;   /* scheduling hint: 0 = whole device, else cap on the persistent grid (a GEMM run beside another)  */
 } ub_gemm_epilogue;
 
 /* a_mn_major / b_mn_major = 1: the operand is stored transposed, i.e. A is [K, lda>=M] / B is [K, ldb>=N]

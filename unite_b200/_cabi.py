@@ -24,6 +24,8 @@ class GemmEpilogue(C.Structure):
         ("act", C.c_int32),
         ("out_fp32", C.c_int32),
         ("accumulate", C.c_int32),
+        ("tile_ctas", C.c_int32),
+        ("max_ctas", C.c_int32),
     ]
 
 

@@ -232,20 +232,30 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const bf16* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // backward, part 0:  D[seq,h,row] = sum_d dO * O
 // ------------------------------------------------------------------------------------------------
-__global__ void attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ D,
-                                     int n_rows, int S, int H) {
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o,
+                                                            float* __restrict__ D, long n_chunks, int S, int H) {
   pdl_grid_sync();
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= n_rows) return;
-  const int seq = row / S, r = row % S;
-  const uint32_t* po = reinterpret_cast<const uint32_t*>(o + (int64_t)row * H * HD);
-  const uint32_t* pd = reinterpret_cast<const uint32_t*>(d_o + (int64_t)row * H * HD);
-  for (int h = 0; h < H; ++h) {
-    const float2 a = unpack_bf16x2(po[h * 32 + lane]);
-    const float2 b = unpack_bf16x2(pd[h * 32 + lane]);
-    const float v = warp_sum(a.x * b.x + a.y * b.y);
-    if (lane == 0) D[((int64_t)seq * H + h) * S + r] = v;
+  // one thread = 8 consecutive channels (16 B of o and of d_o); 8 threads = one (row, head); 3 shuffles finish the dot product
+  const long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  float v = 0.f;
+  if (id < n_chunks) {
+    const uint4 a = ldg_nc_v4(o + id * 8), b = ldg_nc_v4(d_o + id * 8);
+    float2 x, y;
+    x = unpack_bf16x2(a.x); y = unpack_bf16x2(b.x); v = x.x * y.x + x.y * y.y;
+    x = unpack_bf16x2(a.y); y = unpack_bf16x2(b.y); v += x.x * y.x + x.y * y.y;
+    x = unpack_bf16x2(a.z); y = unpack_bf16x2(b.z); v += x.x * y.x + x.y * y.y;
+    x = unpack_bf16x2(a.w); y = unpack_bf16x2(b.w); v += x.x * y.x + x.y * y.y;
+  }
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  if (id < n_chunks && (threadIdx.x & 7) == 0) {
+    const long rh = id >> 3;                       // row * H + head
+    const long row = rh / H;
+    const int h = (int)(rh % H);
+    const long seq = row / S;
+    const int r = (int)(row % S);
+    D[(seq * H + h) * S + r] = v;
   }
 }
 
@@ -583,7 +593,8 @@ extern "C" int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, cons
   UB_REQUIRE(n_seq > 0 && S > 0 && H > 0, "attn_bwd: bad shape n_seq=%d S=%d H=%d", n_seq, S, H);
   cudaStream_t st = (cudaStream_t)stream;
   const int n_rows = n_seq * S;
-  UB_LAUNCH(attn_bwd_prep_kernel, (n_rows + 7) / 8, 256, 0, st, (const bf16*)o, (const bf16*)d_o, D_ws, n_rows, S, H);
+  const long n_chunks = (long)n_rows * H * 8;
+  UB_LAUNCH(attn_bwd_prep_kernel, (unsigned)((n_chunks + 255) / 256), 256, 0, st, (const bf16*)o, (const bf16*)d_o, D_ws, n_chunks, S, H);
   if (check_launch("attn_bwd_prep_kernel")) return 1;
   // short sequences (the student's <= 320 visible tokens): single-pass tcgen05 / TMEM kernel
   static int use_tc = -1;

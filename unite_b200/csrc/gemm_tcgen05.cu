@@ -613,6 +613,10 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   }
   if (force_ncta == 1) ncta = 1;
   if (force_ncta == 2 && bn == 256) ncta = 2;
+  // per-call hint (beats the environment): used when two GEMMs are run side by side on disjoint sets of SMs
+  if (ep.tile_ctas == 1) ncta = 1;
+  if (ep.tile_ctas == 2 && bn == 256 && M > BM) ncta = 2;
+  if (ep.tile_ctas == 4 && bn == 256 && M >= 4 * BM && units4 > 0) ncta = 4;
 
   const int epi = ep.residual != nullptr ? 1 : (ep.act == UB_ACT_DGELU ? 2 : 0);
   const bool out32 = ep.out_fp32 != 0;
@@ -641,7 +645,8 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   p.bias = ep.bias; p.row_scale = ep.row_scale; p.rows_per_scale = ep.rows_per_scale;
   p.act = ep.act; p.accumulate = ep.accumulate; p.has_aux_out = ep.aux_out != nullptr;
   const long total_work = (long)((M + BM * ncta - 1) / (BM * ncta)) * ((N + bn - 1) / bn) * split_k;
-  const int units = ncta == 4 ? units4 : sms / ncta;
+  int units = ncta == 4 ? units4 : sms / ncta;
+  if (ep.max_ctas > 0 && ep.max_ctas / ncta >= 1 && ep.max_ctas / ncta < units) units = ep.max_ctas / ncta;
   const int grid = (int)(total_work < units ? total_work : units) * ncta;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 

@@ -68,7 +68,8 @@ def _p2d(t: torch.Tensor, dtype, what):
 
 @_instrument("gemm", 1)
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=False, bias=None, residual=None,
-         row_scale=None, rows_per_scale=0, act=UB_ACT_NONE, aux_in=None, aux_out=None, accumulate=False, split_k=1):
+         row_scale=None, rows_per_scale=0, act=UB_ACT_NONE, aux_in=None, aux_out=None, accumulate=False, split_k=1, tile_ctas=0,
+         max_ctas=0):
     """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).  a_t / b_t: the operand is stored transposed ([K,M] / [K,N])."""
     pa, lda = _p2d(a, BF16, "gemm A")
     pb, ldb = _p2d(b, BF16, "gemm B")
@@ -103,6 +104,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=
     ep.act = act
     ep.out_fp32 = 1 if out.dtype == F32 else 0
     ep.accumulate = 1 if accumulate else 0
+    ep.tile_ctas, ep.max_ctas = tile_ctas, max_ctas
     check(lib.ub_gemm_bf16(pa, lda, int(a_t), pb, ldb, int(b_t), pc, ldc, M, N, K, C.byref(ep), split_k, _stream()), "ub_gemm_bf16")
     return out
 
