@@ -51,6 +51,8 @@ typedef struct ub_gemm_epilogue {
   int32_t accumulate; /* 1: C (fp32) += result with red.add (required when split_k > 1)                   */
   int32_t tile_ctas;  /* scheduling hint: 0 = cost model, 1 / 2 / 4 = CTAs per work item (4 = two pairs + B multicast) */
   int32_t max_ctas;   /* scheduling hint: 0 = whole device, else cap on the persistent grid (a GEMM run beside another)  */
+  int32_t residual_f16; /* 1: `residual` is fp16 [M, ldr] and C is fp16 too (out_fp32 must be 0): the teacher's residual stream */
+  int32_t reserved;
 } ub_gemm_epilogue;
 
 /* a_mn_major / b_mn_major = 1: the operand is stored transposed, i.e. A is [K, lda>=M] / B is [K, ldb>=N]
@@ -89,11 +91,14 @@ UB_API int ub_cls_attn(const void* qkv, float* out, int n_seq, int S, int H, flo
  *                      bwd takes the upstream gradient as go_scale * go.
  *   ub_l2norm_rows     x /= ||x|| per row (clip.py:173).
  * ---------------------------------------------------------------------------------------------- */
-UB_API int ub_layernorm_fwd(const float* x, const int* src_rows, const float* gamma, const float* beta, float eps,
+/* x: fp32 rows, or fp16 rows when x_f16 != 0 (the frozen teacher keeps its residual stream in fp16, as the reference's
+ * autocast does; statistics are fp32 either way) */
+UB_API int ub_layernorm_fwd(const void* x, int x_f16, const int* src_rows, const float* gamma, const float* beta, float eps,
                             const float* post_add, const int* post_idx, void* out, int out_fp32, int rows, int D,
                             void* stream);
+/* out: fp32, or fp16 when out_f16 != 0 */
 UB_API int ub_teacher_embed_ln(const float* E, const float* cls, const float* pos, const float* gamma, const float* beta,
-                               float eps, float* out, int frames, int P, int D, void* stream);
+                               float eps, void* out, int out_f16, int frames, int P, int D, void* stream);
 UB_API int ub_layernorm_bwd(const void* dy, const float* x, const float* gamma, float eps, const float* dx_in,
                             float* dx_out, void* dxs_out, const float* row_scale, int rows_per_scale, float* dgamma,
                             float* dbeta, float* dsum /* optional: += column sums of dxs (fp32) */, int rows, int D,

@@ -26,6 +26,8 @@ class GemmEpilogue(C.Structure):
         ("accumulate", C.c_int32),
         ("tile_ctas", C.c_int32),
         ("max_ctas", C.c_int32),
+        ("residual_f16", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -51,8 +53,8 @@ SIGNATURES = {
     "ub_attn_fwd": (C.c_int, [_P, _P, _P, _I, _I, _I, _F, _P]),
     "ub_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "ub_cls_attn": (C.c_int, [_P, _P, _I, _I, _I, _F, _P]),
-    "ub_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P]),
-    "ub_teacher_embed_ln": (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _P]),
+    "ub_layernorm_fwd": (C.c_int, [_P, _I, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P]),
+    "ub_teacher_embed_ln": (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _P]),
     "ub_layernorm_bwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P]),
     "ub_dec_tail_fwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _F, _I, _I, _P]),
     "ub_dec_tail_bwd": (C.c_int, [_P, _P, _P, _F, _P, _F, _P, _P, _P, _I, _I, _P]),

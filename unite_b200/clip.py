@@ -21,6 +21,13 @@ from . import ops
 from .modeling_finetune import _ParamsOnly
 
 BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+# Residual stream of the (frozen, inference-only) teacher: fp16, which is what the reference's torch.cuda.amp.autocast region
+# keeps it in (run_stage1.py:360-377 runs the teacher under autocast; clip.LayerNorm casts to fp32 and back, clip.py:20-26).
+# Against the fp32 oracle it costs 7.7e-4 mean / 1.0e-3 max per-token feature error (simulated on the CPU oracle, ViT-B/16)
+# next to the 5e-3 the bf16 GEMM operands cost; it halves the bytes of every LayerNorm read and residual epilogue.
+# UB_TEACHER_STREAM=fp32 restores the fp32 stream.
+import os as _os
+STREAM = F32 if _os.environ.get("UB_TEACHER_STREAM", "fp16") == "fp32" else torch.float16
 
 
 class LayerNorm(nn.LayerNorm):
@@ -106,7 +113,7 @@ class VisionTransformer(nn.Module):
             K = len(self.transformer.return_index)
             self._bufs[key] = dict(
                 E=torch.empty(frames * P, W, device=dev, dtype=F32),
-                x=[torch.empty(R, W, device=dev, dtype=F32) for _ in range(K + 2)],   # work, mid, K snapshots
+                x=[torch.empty(R, W, device=dev, dtype=STREAM) for _ in range(K + 2)],   # work, mid, K snapshots
                 h=torch.empty(R, W, device=dev, dtype=BF16), qkv=torch.empty(R, 3 * W, device=dev, dtype=BF16),
                 o=torch.empty(R, W, device=dev, dtype=BF16), u=torch.empty(R, 4 * W, device=dev, dtype=BF16))
         return self._bufs[key]
@@ -180,9 +187,9 @@ class VisionTransformer(nn.Module):
         key = ("tail", n)
         if key not in self._bufs:
             dev, W = self.proj.device, self.width
-            self._bufs[key] = dict(o=torch.empty(n, W, device=dev, dtype=BF16), x=torch.empty(n, W, device=dev, dtype=F32),
-                                   mid=torch.empty(n, W, device=dev, dtype=F32), h=torch.empty(n, W, device=dev, dtype=BF16),
-                                   u=torch.empty(n, 4 * W, device=dev, dtype=BF16), out=torch.empty(n, W, device=dev, dtype=F32))
+            self._bufs[key] = dict(o=torch.empty(n, W, device=dev, dtype=BF16), x=torch.empty(n, W, device=dev, dtype=STREAM),
+                                   mid=torch.empty(n, W, device=dev, dtype=STREAM), h=torch.empty(n, W, device=dev, dtype=BF16),
+                                   u=torch.empty(n, 4 * W, device=dev, dtype=BF16), out=torch.empty(n, W, device=dev, dtype=STREAM))
         return self._bufs[key]
 
     @torch.no_grad()

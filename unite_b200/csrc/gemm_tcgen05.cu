@@ -18,6 +18,7 @@
 //     contracted over their ROW index: dgrad uses W as B^T, wgrad contracts over tokens) — no transposes
 //     are ever materialised.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -42,7 +43,8 @@ struct GemmParams {
   int has_aux_out;
 };
 
-// EPI : 0 = bias / activation (/ pre-activation copy), 1 = + fp32 residual (fp32 out), 2 = DGELU: * gelu'(aux) (bf16 out)
+// EPI : 0 = bias / activation (/ pre-activation copy), 1 = + fp32 residual (fp32 out), 2 = DGELU: * gelu'(aux) (bf16 out),
+//       3 = + fp16 residual (fp16 out: the frozen teacher's residual stream)
 // OUT32: C is fp32 (32-column slabs) or bf16 (64-column slabs); both give 128-byte staging rows
 // NCTA: 1 = one CTA per 128 x BN tile; 2 = CTA pair per 256 x BN tile; 4 = cluster of two pairs on a 512 x BN tile that
 //       share B: each CTA fetches a quarter of the B tile and TMA-multicasts it to the CTA of the same rank in the other pair
@@ -64,6 +66,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int SLABS = (BN / 2) / CW;       // slabs per warp per tile
   static_assert(EPI != 1 || OUT32, "residual epilogue writes fp32");
   static_assert(EPI != 2 || !OUT32, "DGELU epilogue writes bf16");
+  static_assert(EPI != 3 || !OUT32, "the fp16-residual epilogue writes fp16");
   const uint32_t cta_rank = NCTA >= 2 ? cluster_ctarank() : 0u;
   const uint32_t pr = cta_rank & (CG - 1);          // rank inside the pair
   const uint32_t pp = cta_rank / CG;                // pair inside the cluster
@@ -361,6 +364,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                            "f"(v[4 * j + 3])
                            : "memory");
             }
+          } else if (EPI == 3) {
+            // fp16 slab: the residual that TMA placed here is read, added in fp32 and replaced by the fp16 sum
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t a = slab0_a + ((uint32_t)b << 12) + rowoff + ((((uint32_t)(h * 4 + j)) ^ sw) << 4);
+              uint4 pk;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "r"(a));
+              const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&pk.x)), r1 = __half22float2(*reinterpret_cast<const __half2*>(&pk.y));
+              const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&pk.z)), r3 = __half22float2(*reinterpret_cast<const __half2*>(&pk.w));
+              const __half2 o0 = __floats2half2_rn(v[8 * j] + r0.x, v[8 * j + 1] + r0.y), o1 = __floats2half2_rn(v[8 * j + 2] + r1.x, v[8 * j + 3] + r1.y);
+              const __half2 o2 = __floats2half2_rn(v[8 * j + 4] + r2.x, v[8 * j + 5] + r2.y), o3 = __floats2half2_rn(v[8 * j + 6] + r3.x, v[8 * j + 7] + r3.y);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(*reinterpret_cast<const uint32_t*>(&o0)),
+                           "r"(*reinterpret_cast<const uint32_t*>(&o1)), "r"(*reinterpret_cast<const uint32_t*>(&o2)),
+                           "r"(*reinterpret_cast<const uint32_t*>(&o3))
+                           : "memory");
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -543,6 +562,7 @@ static int launch_gemm(const GemmMaps& m, const GemmParams& p, int epi, bool out
     if (epi == 0 && !out32) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 0, false, NCTA>(m, p, grid, stream);
     if (epi == 1) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 1, true, NCTA>(m, p, grid, stream);
     if (epi == 2) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 2, false, NCTA>(m, p, grid, stream);
+    if (epi == 3) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 3, false, NCTA>(m, p, grid, stream);
   }
   set_error("gemm: epilogue variant (epi=%d, fp32 out=%d) is not instantiated for operand majors a_mn=%d b_mn=%d", epi, (int)out32,
             (int)A_MN, (int)B_MN);
@@ -568,7 +588,8 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   UB_REQUIRE(ep.row_scale == nullptr || ep.rows_per_scale > 0, "gemm: rows_per_scale must be > 0");
   UB_REQUIRE(ep.act != UB_ACT_DGELU || ep.aux_in != nullptr, "gemm: DGELU needs aux_in");
   UB_REQUIRE(!(ep.act == UB_ACT_DGELU && ep.residual != nullptr), "gemm: DGELU with a residual is not supported");
-  UB_REQUIRE(ep.residual == nullptr || ep.out_fp32, "gemm: the residual epilogue writes fp32");
+  UB_REQUIRE(ep.residual == nullptr || ep.out_fp32 || ep.residual_f16, "gemm: the residual epilogue writes fp32 (or fp16 with residual_f16)");
+  UB_REQUIRE(!ep.residual_f16 || (ep.residual != nullptr && !ep.out_fp32), "gemm: residual_f16 needs a residual and a 2-byte (fp16) output");
   UB_REQUIRE(ep.act != UB_ACT_DGELU || !ep.out_fp32, "gemm: the DGELU epilogue writes bf16");
   UB_REQUIRE(ep.residual == nullptr || (ep.act == UB_ACT_NONE && !ep.accumulate),
              "gemm: residual cannot be combined with an activation / accumulate");
@@ -618,7 +639,7 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   if (ep.tile_ctas == 2 && bn == 256 && M > BM) ncta = 2;
   if (ep.tile_ctas == 4 && bn == 256 && M >= 4 * BM && units4 > 0) ncta = 4;
 
-  const int epi = ep.residual != nullptr ? 1 : (ep.act == UB_ACT_DGELU ? 2 : 0);
+  const int epi = ep.residual != nullptr ? (ep.residual_f16 ? 3 : 1) : (ep.act == UB_ACT_DGELU ? 2 : 0);
   const bool out32 = ep.out_fp32 != 0;
   GemmMaps m;
   memset(&m, 0, sizeof(m));
@@ -636,6 +657,7 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   m.r = m.c;
   m.x = m.c;
   if (epi == 1 && make_tmap_2d(&m.r, ep.residual, M, N, ep.ldr, 32, 32, 4)) return 1;
+  if (epi == 3 && make_tmap_2d(&m.r, ep.residual, M, N, ep.ldr, 64, 32, 2)) return 1;
   if (epi == 2 && make_tmap_2d(&m.r, ep.aux_in, M, N, ep.ld_aux, 64, 32, 2)) return 1;
   if (ep.aux_out != nullptr && make_tmap_2d(&m.x, ep.aux_out, M, N, ep.ld_aux, 64, 32, 2)) return 1;
 

@@ -8,6 +8,7 @@
 // and the autograd backward of the student ones.  Statistics are always fp32; the residual stream is fp32;
 // outputs that feed a GEMM are bf16.  D must be a multiple of 128 and <= 1024.
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include "../../include/unite_b200.h"
 
 namespace ub {
@@ -54,6 +55,30 @@ UB_DEVINL void row_store_bf16(const RowT<NV>& r, bf16* p, int nv, int lane) {
       *reinterpret_cast<uint2*>(p + (i * 32 + lane) * 4) = u;
     }
 }
+// fp16 rows: the frozen teacher keeps its residual stream in fp16 (what the reference's autocast does, clip.py under
+// torch.cuda.amp.autocast); statistics and arithmetic stay fp32
+template <int NV>
+UB_DEVINL void row_load_f16(RowT<NV>& r, const __half* p, int nv, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (i < nv) {
+      const uint2 u = *reinterpret_cast<const uint2*>(p + (i * 32 + lane) * 4);
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      r.v[i] = make_float4(a.x, a.y, b.x, b.y);
+    }
+}
+template <int NV>
+UB_DEVINL void row_store_f16(const RowT<NV>& r, __half* p, int nv, int lane) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (i < nv) {
+      uint2 u;
+      const __half2 a = __floats2half2_rn(r.v[i].x, r.v[i].y), b = __floats2half2_rn(r.v[i].z, r.v[i].w);
+      u.x = *reinterpret_cast<const uint32_t*>(&a);
+      u.y = *reinterpret_cast<const uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(p + (i * 32 + lane) * 4) = u;
+    }
+}
 template <int NV>
 UB_DEVINL float row_sum(const RowT<NV>& r, int nv) {
   float s = 0.f;
@@ -90,7 +115,7 @@ UB_DEVINL float row_center_rstd(RowT<NV>& x, int nv, int D, float eps) {
 // forward:  out[r] = LN(x[src(r)]) * gamma + beta  (+ post_add[post_idx[r]])
 // ------------------------------------------------------------------------------------------------
 struct LnFwdArgs {
-  const float* x;
+  const void* x;          // fp32, or fp16 when x_f16
   const int* src_rows;    // optional gather of input rows
   const float* gamma;
   const float* beta;
@@ -100,6 +125,7 @@ struct LnFwdArgs {
   int out_fp32;
   int rows, D;
   float eps;
+  int x_f16;
 };
 
 template <int NV>
@@ -111,7 +137,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < a.rows; row += gridDim.x * wpb) {
     const int64_t src = a.src_rows ? a.src_rows[row] : row;
     RowT<NV> x;
-    row_load_f32(x, a.x + src * a.D, nv, lane);
+    if (a.x_f16) row_load_f16(x, reinterpret_cast<const __half*>(a.x) + src * a.D, nv, lane);
+    else row_load_f32(x, reinterpret_cast<const float*>(a.x) + src * a.D, nv, lane);
     const float rstd = row_center_rstd(x, nv, a.D, a.eps);
     UB_ROW_FOREACH(i, nv) {   // gamma / beta come from L1 every row: keeps the kernel at ~40 registers -> full occupancy
       float4 g, b;
@@ -140,8 +167,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
 template <int NV>
 __global__ void __launch_bounds__(256) teacher_embed_ln_kernel(const float* __restrict__ E, const float* __restrict__ cls,
                                                                const float* __restrict__ pos, const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta, float* __restrict__ out,
-                                                               int frames, int P, int D, float eps) {
+                                                               const float* __restrict__ beta, void* __restrict__ out,
+                                                               int frames, int P, int D, float eps, int out_f16) {
   pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   constexpr int nv = NV;
@@ -166,7 +193,8 @@ __global__ void __launch_bounds__(256) teacher_embed_ln_kernel(const float* __re
       x.v[i].z = x.v[i].z * rstd * g.v[i].z + b.v[i].z;
       x.v[i].w = x.v[i].w * rstd * g.v[i].w + b.v[i].w;
     }
-    row_store_f32(x, out + (int64_t)row * D, nv, lane);
+    if (out_f16) row_store_f16(x, reinterpret_cast<__half*>(out) + (int64_t)row * D, nv, lane);
+    else row_store_f32(x, reinterpret_cast<float*>(out) + (int64_t)row * D, nv, lane);
   }
 }
 
@@ -416,23 +444,23 @@ static int check_D(int D, const char* who) {
 
 using namespace ub;
 
-extern "C" int ub_layernorm_fwd(const float* x, const int* src_rows, const float* gamma, const float* beta, float eps,
+extern "C" int ub_layernorm_fwd(const void* x, int x_f16, const int* src_rows, const float* gamma, const float* beta, float eps,
                                 const float* post_add, const int* post_idx, void* out, int out_fp32, int rows, int D,
                                 void* stream) {
   UB_REQUIRE(x && gamma && beta && out, "layernorm_fwd: null pointer");
   UB_REQUIRE(rows > 0, "layernorm_fwd: rows=%d", rows);
   UB_REQUIRE((post_add == nullptr) == (post_idx == nullptr), "layernorm_fwd: post_add and post_idx go together");
   if (check_D(D, "layernorm_fwd")) return 1;
-  LnFwdArgs a{x, src_rows, gamma, beta, post_add, post_idx, out, out_fp32, rows, D, eps};
+  LnFwdArgs a{x, src_rows, gamma, beta, post_add, post_idx, out, out_fp32, rows, D, eps, x_f16};
   UB_LN_DISPATCH(D, ln_fwd_kernel, ln_grid(rows), 0, (cudaStream_t)stream, a)
   return check_launch("ln_fwd_kernel");
 }
 
 extern "C" int ub_teacher_embed_ln(const float* E, const float* cls, const float* pos, const float* gamma,
-                                   const float* beta, float eps, float* out, int frames, int P, int D, void* stream) {
+                                   const float* beta, float eps, void* out, int out_f16, int frames, int P, int D, void* stream) {
   UB_REQUIRE(E && cls && pos && gamma && beta && out, "teacher_embed_ln: null pointer");
   if (check_D(D, "teacher_embed_ln")) return 1;
-  UB_LN_DISPATCH(D, teacher_embed_ln_kernel, ln_grid(frames * (P + 1)), 0, (cudaStream_t)stream, E, cls, pos, gamma, beta, out, frames, P, D, eps)
+  UB_LN_DISPATCH(D, teacher_embed_ln_kernel, ln_grid(frames * (P + 1)), 0, (cudaStream_t)stream, E, cls, pos, gamma, beta, out, frames, P, D, eps, out_f16)
   return check_launch("teacher_embed_ln_kernel");
 }
 

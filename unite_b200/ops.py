@@ -13,6 +13,7 @@ from . import _cabi
 from ._cabi import lib, check, GemmEpilogue, UB_ACT_NONE, UB_ACT_QUICKGELU, UB_ACT_GELU, UB_ACT_DGELU  # noqa: F401
 
 BF16, F32, I32, U8 = torch.bfloat16, torch.float32, torch.int32, torch.uint8
+F16 = torch.float16
 
 
 def _stream() -> int:
@@ -73,8 +74,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=
     """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).  a_t / b_t: the operand is stored transposed ([K,M] / [K,N])."""
     pa, lda = _p2d(a, BF16, "gemm A")
     pb, ldb = _p2d(b, BF16, "gemm B")
-    if out.dtype not in (BF16, F32):
-        raise _cabi.UBError("gemm out: bf16 or fp32 expected")
+    if out.dtype not in (BF16, F32, F16):
+        raise _cabi.UBError("gemm out: bf16, fp32 or (with an fp16 residual) fp16 expected")
+    if out.dtype == F16 and (residual is None or residual.dtype != F16):
+        raise _cabi.UBError("gemm out: fp16 output is only produced by the fp16-residual epilogue")
     pc, ldc = _p2d(out, out.dtype, "gemm C")
     M, N = out.shape
     K = a.shape[0] if a_t else a.shape[1]
@@ -88,7 +91,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=
             raise _cabi.UBError("gemm bias: wrong length")
         ep.bias = _p(bias, F32, "gemm bias")
     if residual is not None:
-        pr, ldr = _p2d(residual, F32, "gemm residual")
+        if residual.dtype == F16:
+            if out.dtype != F16:
+                raise _cabi.UBError("gemm: an fp16 residual needs an fp16 output (the teacher's residual stream)")
+            ep.residual_f16 = 1
+        pr, ldr = _p2d(residual, residual.dtype if residual.dtype == F16 else F32, "gemm residual")
         if tuple(residual.shape) != (M, N):
             raise _cabi.UBError("gemm residual: wrong shape")
         ep.residual, ep.ldr = pr, ldr
@@ -128,7 +135,9 @@ def cls_attn(qkv, out, n_seq, S, H, scale):
 @_instrument("layernorm_fwd", 1)
 def layernorm_fwd(x, gamma, beta, eps, out, *, src_rows=None, post_add=None, post_idx=None):
     rows, D = out.shape
-    check(lib.ub_layernorm_fwd(_p(x, F32, "ln x"), _p(src_rows, I32, "src_rows"), _p(gamma, F32, "gamma"), _p(beta, F32, "beta"),
+    if x.dtype not in (F32, F16):
+        raise _cabi.UBError(f"ln x: fp32 or fp16 rows expected, got {x.dtype}")
+    check(lib.ub_layernorm_fwd(_p(x, None, "ln x"), 1 if x.dtype == F16 else 0, _p(src_rows, I32, "src_rows"), _p(gamma, F32, "gamma"), _p(beta, F32, "beta"),
                                eps, _p(post_add, F32, "post_add"), _p(post_idx, I32, "post_idx"), _p(out, None, "ln out"),
                                1 if out.dtype == F32 else 0, rows, D, _stream()), "ub_layernorm_fwd")
     return out
@@ -137,7 +146,8 @@ def layernorm_fwd(x, gamma, beta, eps, out, *, src_rows=None, post_add=None, pos
 @_instrument("teacher_embed_ln", 1)
 def teacher_embed_ln(E, cls, pos, gamma, beta, eps, out, frames, P, D):
     check(lib.ub_teacher_embed_ln(_p(E, F32, "E"), _p(cls, F32, "cls"), _p(pos, F32, "pos"), _p(gamma, F32, "gamma"),
-                                  _p(beta, F32, "beta"), eps, _p(out, F32, "out"), frames, P, D, _stream()), "ub_teacher_embed_ln")
+                                  _p(beta, F32, "beta"), eps, _p(out, None, "out"), 1 if out.dtype == F16 else 0, frames, P, D, _stream()),
+          "ub_teacher_embed_ln")
 
 
 @_instrument("layernorm_bwd", 1)
