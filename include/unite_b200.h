@@ -130,7 +130,8 @@ UB_API int ub_mask_select(const float* attn, const float* q, uint8_t* mask, int*
                           int P, int T, int k, int n_vis, void* stream);
 UB_API int ub_gather_rows(const void* in, const int* idx, void* out, int64_t n_rows, int64_t row_bytes,
                           int rows_per_group, int64_t group_stride_rows, void* stream);
-UB_API int ub_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, void* stream);
+/* columns [skip_lo, skip_hi) are not accumulated (pass 0, 0 for none): the key third of the q|k|v bias has no gradient */
+UB_API int ub_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, int skip_lo, int skip_hi, void* stream);
 UB_API int ub_cast_scale_bf16(const float* x, void* out, const float* row_scale, int rows_per_scale, int64_t rows, int D,
                               void* stream);
 

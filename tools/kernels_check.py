@@ -181,6 +181,10 @@ def check_tokens():
     x = torch.randn(1000, 2304, device=dev, generator=g).bfloat16(); cs = torch.zeros(2304, device=dev)
     ops.colsum_bf16(x, cs)
     report("colsum_bf16", cs, x.float().sum(0), 1e-5)
+    cs2 = torch.full((2304,), 7.0, device=dev)
+    ops.colsum_bf16(x, cs2, skip=(768, 1536))             # the key third of a q|k|v bias gradient is left untouched
+    ref2 = x.float().sum(0) + 7.0; ref2[768:1536] = 7.0
+    report("colsum_bf16 skip range", cs2, ref2, 1e-5)
     xf = torch.randn(640, 768, device=dev, generator=g); o16 = torch.empty(640, 768, device=dev, dtype=torch.bfloat16)
     rs = torch.rand(4, device=dev, generator=g)
     ops.cast_scale_bf16(xf, o16, rs, 160)

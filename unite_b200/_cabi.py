@@ -63,7 +63,7 @@ SIGNATURES = {
     "ub_patchify_u8": (C.c_int, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _I, _I, _I, _I, _P]),
     "ub_mask_select": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "ub_gather_rows": (C.c_int, [_P, _P, _P, _L, _L, _I, _L, _P]),
-    "ub_colsum_bf16": (C.c_int, [_P, _L, _P, _I, _I, _P]),
+    "ub_colsum_bf16": (C.c_int, [_P, _L, _P, _I, _I, _I, _I, _P]),
     "ub_cast_scale_bf16": (C.c_int, [_P, _P, _P, _I, _L, _I, _P]),
     "ub_sumsq": (C.c_int, [_P, _L, _P, _P]),
     "ub_adamw": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _F, _F, _F, _F, _F, _I, _F, _P]),

@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint4* __restric
 // through smem and issues one red.add per column.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ x, int64_t ld, float* __restrict__ out,
-                                                          int M, int N, int CS_ROWS) {
+                                                          int M, int N, int CS_ROWS, int skip_lo, int skip_hi) {
   pdl_grid_sync();
   __shared__ float s_part[8][256];
   const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
   for (int i = 0; i < 8; ++i) s_part[rg][lane * 8 + i] = acc[i];
   __syncthreads();
   const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < N) {
+  if (c < N && !(c >= skip_lo && c < skip_hi)) {      // skipped columns (the structurally zero key bias) are left untouched
     float s = 0.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) s += s_part[g][threadIdx.x];
@@ -281,7 +281,7 @@ extern "C" int ub_gather_rows(const void* in, const int* idx, void* out, int64_t
   return check_launch("gather_rows_kernel");
 }
 
-extern "C" int ub_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, void* stream) {
+extern "C" int ub_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, int skip_lo, int skip_hi, void* stream) {
   UB_REQUIRE(x && out && M > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, "colsum_bf16: N and ld must be multiples of 8 (M=%d N=%d)", M, N);
   UB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "colsum_bf16: x must be 16-byte aligned");
   // rows per CTA (multiple of 32): small enough that the grid keeps ~6 CTAs per SM in flight — this is a latency-bound pass
@@ -291,7 +291,7 @@ extern "C" int ub_colsum_bf16(const void* x, int64_t ld, float* out, int M, int 
   int rows = ((M + want_y - 1) / want_y + 31) / 32 * 32;
   rows = rows < 32 ? 32 : (rows > 128 ? 128 : rows);
   dim3 grid(gx, (M + rows - 1) / rows);
-  UB_LAUNCH(colsum_bf16_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16*)x, ld, out, M, N, rows);
+  UB_LAUNCH(colsum_bf16_kernel, grid, 256, 0, (cudaStream_t)stream, (const bf16*)x, ld, out, M, N, rows, skip_lo, skip_hi);
   return check_launch("colsum_bf16_kernel");
 }
 

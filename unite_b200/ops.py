@@ -221,10 +221,11 @@ def gather_rows(src, idx, out, rows_per_group=0, group_stride_rows=0):
 
 
 @_instrument("colsum_bf16", 1)
-def colsum_bf16(x, out):
+def colsum_bf16(x, out, skip=(0, 0)):
+    """out[n] += sum_m x[m, n]; columns skip[0] <= n < skip[1] are left untouched."""
     px, ld = _p2d(x, BF16, "colsum x")
     M, N = x.shape
-    check(lib.ub_colsum_bf16(px, ld, _p(out, F32, "colsum out"), M, N, _stream()), "ub_colsum_bf16")
+    check(lib.ub_colsum_bf16(px, ld, _p(out, F32, "colsum out"), M, N, skip[0], skip[1], _stream()), "ub_colsum_bf16")
 
 
 @_instrument("cast_scale_bf16", 1)

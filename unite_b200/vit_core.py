@@ -229,10 +229,8 @@ class ViTTrunk:
             ops.gemm(dqkv, self.w(b + "attn.qkv.weight"), ws.d_h, b_t=True)
             wgrad(dqkv, L.h1, self.g(b + "attn.qkv.weight"))
             # q_bias | (always-zero k gap) | v_bias are one contiguous 3D span of the gradient arena: one column-sum pass
-            # over all of dqkv, then clear the gap (the key bias is structurally zero, modeling_finetune.py:104)
-            gq = self.qkv_bias_grad(l)
-            ops.colsum_bf16(dqkv, gq)
-            gq[D:2 * D].zero_()
+            # over dqkv that leaves the gap alone (the key bias is structurally zero, modeling_finetune.py:104)
+            ops.colsum_bf16(dqkv, self.qkv_bias_grad(l), skip=(D, 2 * D))
             # next consumer of dxs: block l-1's MLP branch (unless a tap re-emits it) or the patch embedding
             emit = (l - 1) not in tap_grads
             s_next = None if (dp is None or l == 0) else dp[l - 1, 1]
