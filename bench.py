@@ -278,6 +278,10 @@ def main():
     if rank == 0:
         ops.PROFILE = []
     eng.use_graph = False              # the instrumented step runs eagerly (events around every launch)
+    # Eagerly, the host needs ~10 us per launch and the GPU would idle INSIDE the event pairs waiting for the next command
+    # (that inflated the per-kernel times of earlier rounds' JSON by 3-5 us per launch).  A spin kernel ahead of the step lets
+    # the host queue the whole step first, so every event pair brackets device execution only.
+    torch.cuda._sleep(int(0.15 * 1.9e9))
     eng.step(*dev_batches[0])          # every rank runs it (the step contains the all-reduce); only rank 0 records
     sync_all()
     if rank == 0:
