@@ -284,9 +284,18 @@ def student_forward(sd: SD, x: Tensor, mask: Tensor, cfg: StudentCfg, clip_only:
     return x_vis, x_clip
 
 
-def alignment_loss(outputs: Tensor, targets: Tensor) -> Tensor:
-    """clip_loss_type == 'l2' (run_stage1.py:430-431)."""
-    return (2 - 2 * (outputs * targets).sum(dim=-1)).mean()
+def alignment_loss(outputs: Tensor, targets: Tensor, kind: str = "l2") -> Tensor:
+    """run_stage1.py:430-433: 'l2' is the cosine form of the shipped config; 'mse' / 'smooth_l1' / 'l1' are the
+    nn.MSELoss / nn.SmoothL1Loss / nn.L1Loss instances built at :403-408 (default reduction 'mean', beta 1)."""
+    if kind == "l2":
+        return (2 - 2 * (outputs * targets).sum(dim=-1)).mean()
+    if kind == "mse":
+        return F.mse_loss(outputs, targets)
+    if kind == "smooth_l1":
+        return F.smooth_l1_loss(outputs, targets)
+    if kind == "l1":
+        return F.l1_loss(outputs, targets)
+    raise NotImplementedError(kind)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -294,7 +303,7 @@ def alignment_loss(outputs: Tensor, targets: Tensor) -> Tensor:
 # --------------------------------------------------------------------------------------------------
 def stage1_step(student_sd: SD, teacher_sd: SD, videos: Tensor, q: Tensor, scfg: StudentCfg, tcfg: TeacherCfg,
                 mask_ratio: float = 0.8, keep_scales: Optional[Tensor] = None, with_grads: bool = True,
-                attn_override: Optional[Tensor] = None):
+                attn_override: Optional[Tensor] = None, clip_loss_type: str = "l2"):
     """One UMT masked-distillation step with mask_type='attention', clip_loss_type='l2',
     clip_loss_data='mixed', src_classifier=None.  q = Exp(1) noise [B*T', HW] consumed by the mask sampler.
     Returns a dict with every intermediate the parity tests compare."""
@@ -307,7 +316,7 @@ def stage1_step(student_sd: SD, teacher_sd: SD, videos: Tensor, q: Tensor, scfg:
         targets = feat[~mask.unsqueeze(0).repeat(K, 1, 1)].reshape(K, B, -1, C)        # :389-393
     params = {k: v.detach().clone().requires_grad_(with_grads) for k, v in student_sd.items()}
     out = student_forward(params, videos, mask, scfg, clip_only=True, keep_scales=keep_scales)   # :415
-    loss = alignment_loss(out, targets)                                                # :431
+    loss = alignment_loss(out, targets, clip_loss_type)                               # :430-433
     res = dict(attn=attn, mask=mask, vis_idx=visible_indices(mask), targets=targets, outputs=out.detach(),
                loss=loss.detach())
     if with_grads:

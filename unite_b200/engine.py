@@ -87,12 +87,13 @@ class FusedAdamW:
 class Stage1Engine:
     def __init__(self, student: AdaptationVisionTransformer, teacher: ClipVisionTransformer, mask_ratio: float = 0.8,
                  lr: float = 1.5e-4, weight_decay: float = 0.05, betas=(0.9, 0.95), eps: float = 1e-8, grad_sync=None,
-                 use_graph: bool = False):
+                 use_graph: bool = False, clip_loss_type: str = "l2"):
         """use_graph: after two eager steps of a given batch shape, the whole step (teacher, mask, student fwd/bwd,
         gradient all-reduce, grad-norm, AdamW) is captured once in a CUDA graph and replayed — the ~460 launches of a step
         then cost one launch.  Requires DropPath off (random draws inside a captured region would be frozen)."""
         self.student, self.teacher, self.mask_ratio = student, teacher, mask_ratio
         self.use_graph = use_graph
+        self.clip_loss_type = clip_loss_type
         self._graphs = {}
         self._eager_steps = {}
         self.core = student.core()
@@ -107,7 +108,7 @@ class Stage1Engine:
         return P - int(P * self.mask_ratio)                      # run_stage1.py:380
 
     def forward_backward(self, videos: torch.Tensor, q: torch.Tensor, dp: Optional[torch.Tensor] = None,
-                         attn_override: Optional[torch.Tensor] = None):
+                         attn_override: Optional[torch.Tensor] = None, clip_loss_type: Optional[str] = None):
         """Everything up to (not including) the optimizer.  videos fp32 [B,3,T,H,W] on the device; q fp32 [B*T',HW]
         Exp(1) noise for the mask sampler.  Returns the device loss tensor [1]."""
         core, teacher = self.core, self.teacher
@@ -155,9 +156,31 @@ class Stage1Engine:
         self.loss.zero_()
         if patches_s is None:
             patches_s = patches if self.share_patches else None
-        _, x_clip, state = core.run_forward(videos, vis_idx[0], patches_s, dp, True, True,
-                                            targets=targets, loss_acc=self.loss)
-        core.run_backward(state, targets=targets, grad_sync=self.grad_sync)
+        kind = clip_loss_type or self.clip_loss_type
+        if kind == "l2":
+            # shipped config: the loss and its gradient are fused into the decoder-tail kernels
+            _, x_clip, state = core.run_forward(videos, vis_idx[0], patches_s, dp, True, True,
+                                                targets=targets, loss_acc=self.loss)
+            core.run_backward(state, targets=targets, grad_sync=self.grad_sync)
+        else:
+            # run_stage1.py:403-408,432-433 (nn.MSELoss / nn.SmoothL1Loss / nn.L1Loss, mean reduction): loss value and
+            # d loss / d outputs are a few element-wise device ops on the [K,B,Nv,C] outputs; the rest of backward is shared
+            _, x_clip, state = core.run_forward(videos, vis_idx[0], patches_s, dp, True, True)
+            d = x_clip - targets.view_as(x_clip)
+            n = d.numel()
+            if kind == "mse":
+                self.loss += (d * d).sum() / n
+                g = d * (2.0 / n)
+            elif kind == "smooth_l1":
+                ad = d.abs()
+                self.loss += torch.where(ad < 1.0, 0.5 * d * d, ad - 0.5).sum() / n
+                g = d.clamp(-1.0, 1.0) / n
+            elif kind == "l1":
+                self.loss += d.abs().sum() / n
+                g = d.sign() / n
+            else:
+                raise NotImplementedError(f"clip_loss_type={kind!r} (run_stage1.py:430-435 raises for anything else too)")
+            core.run_backward(state, g_clip=g, grad_sync=self.grad_sync)
         self.last = dict(attn=attn, mask=mask.view(B, Tp * P).bool(), vis_idx=vis_idx[0], targets=targets, outputs=x_clip)
         return self.loss
 
@@ -178,7 +201,7 @@ class Stage1Engine:
                 scale = self.grad_sync.all_reduce(self.core.arena.grads)
             self.optimizer.step(grad_scale=scale)
             return loss
-        key = (tuple(videos.shape), tuple(q.shape))
+        key = (tuple(videos.shape), videos.dtype, tuple(q.shape), self.clip_loss_type)
         scale = 1.0 / self.grad_sync.world if self.grad_sync is not None else 1.0
         self.optimizer.prepare_step(grad_scale=scale)
         if key not in self._graphs:

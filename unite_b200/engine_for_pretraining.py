@@ -37,13 +37,18 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
                     lr_scheduler=None, start_steps=0, lr_schedule_values=None, wd_schedule_values=None, src_classifier=None,
                     teacher_model=None, clip_input_resolution=224, clip_loss_type="l2", clip_loss_ratio=0.5,
                     mask_type="attention", mask_ratio=0.0, use_wandb=False, args=None):
-    if mask_type != "attention" or clip_loss_type != "l2" or src_classifier is not None:
-        raise NotImplementedError("the fused stage-1 path covers the shipped config: mask_type='attention', clip_loss_type='l2', "
-                                  "no source classifier (configs/stage1_config.yaml)")
+    if mask_type != "attention" or src_classifier is not None:
+        # (the reference itself only runs with mask_type='attention': run_stage1.py:378 reads `attn`, which the other mask
+        # types never define)
+        raise NotImplementedError("the fused stage-1 path covers mask_type='attention' without a source classifier "
+                                  "(configs/stage1_config.yaml)")
+    if clip_loss_type not in ("l2", "mse", "smooth_l1", "l1"):
+        raise NotImplementedError(f"clip_loss_type={clip_loss_type!r}")                  # run_stage1.py:434-435
     if max_norm:
         raise NotImplementedError("clip_grad is null in every shipped config")
     model.train()
     eng = _engine_for(model, teacher_model, mask_ratio, optimizer, use_graph=bool(getattr(args, "use_cuda_graph", False)))
+    eng.clip_loss_type = clip_loss_type
     opt = eng.optimizer
     dev = eng.core.arena.device
     log_freq = getattr(args, "log_freq", 10) if args is not None else 10
