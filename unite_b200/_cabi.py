@@ -6,7 +6,9 @@ not been built — there is no Python/torch fallback for any op on the product p
 import ctypes as C
 import os
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libunite_b200.so")
+# UB_LIB_VARIANT=<suffix> loads lib/libunite_b200_<suffix>.so instead (A/B runs of two builds on one GPU box)
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                         "libunite_b200%s.so" % ("_" + os.environ["UB_LIB_VARIANT"] if os.environ.get("UB_LIB_VARIANT") else ""))
 
 UB_ACT_NONE, UB_ACT_QUICKGELU, UB_ACT_GELU, UB_ACT_DGELU = 0, 1, 2, 3
 

@@ -185,10 +185,17 @@ UB_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
+#ifdef UB_MBAR_SUSPEND_HINT
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#endif
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
+#ifdef UB_MBAR_SUSPEND_HINT
+        , "r"((uint32_t)UB_MBAR_SUSPEND_HINT)
+#endif
       : "memory");
   return ok != 0;
 }
