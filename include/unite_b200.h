@@ -27,6 +27,10 @@ extern "C" {
 UB_API int ub_version(void);
 UB_API const char* ub_last_error(void);
 UB_API int ub_sm_count(void);
+/* Size every persistent grid of the library for n SMs instead of the whole device (0 = whole device); returns the count now in
+ * effect.  Data-parallel runs leave a few SMs to the NCCL all-reduce that overlaps backward (unite_b200/ddp.py): a persistent
+ * kernel whose static schedule assumes 148 resident CTAs stalls for the whole collective if 4 of them cannot be placed. */
+UB_API int ub_set_sm_limit(int n);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM (tcgen05/TMEM/TMA):  C[M,N] = epilogue( A[M,K] * B[N,K]^T )      bf16 x bf16 -> fp32 accumulate

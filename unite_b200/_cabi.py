@@ -50,6 +50,7 @@ SIGNATURES = {
     "ub_version": (C.c_int, []),
     "ub_last_error": (C.c_char_p, []),
     "ub_sm_count": (C.c_int, []),
+    "ub_set_sm_limit": (C.c_int, [_I]),
     "ub_gemm_cluster4_capacity": (C.c_int, []),
     "ub_gemm_bf16": (C.c_int, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, C.POINTER(GemmEpilogue), _I, _P]),
     "ub_attn_fwd": (C.c_int, [_P, _P, _P, _I, _I, _I, _F, _P]),

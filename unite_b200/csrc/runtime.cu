@@ -25,6 +25,8 @@ int check_launch(const char* what) {
   return 0;
 }
 
+static int g_sm_limit = 0;   // 0 = all SMs; otherwise the persistent grids leave the rest to a concurrent collective
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -32,7 +34,7 @@ int sm_count() {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = 148;
   }
-  return n;
+  return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 bool pdl_enabled() {
@@ -49,3 +51,7 @@ bool pdl_enabled() {
 extern "C" int ub_version(void) { return 100; }
 extern "C" const char* ub_last_error(void) { return ub::g_err; }
 extern "C" int ub_sm_count(void) { return ub::sm_count(); }
+extern "C" int ub_set_sm_limit(int n) {
+  ub::g_sm_limit = n > 0 ? (n & ~1) : 0;     // even, so CTA pairs still tile it
+  return ub::sm_count();
+}

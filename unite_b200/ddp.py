@@ -14,6 +14,12 @@ import torch
 import torch.distributed as dist
 
 
+import os as _os
+
+# UB_DDP_OVERLAP=0: one all-reduce of the whole arena after backward instead of per-block ranges overlapped with it
+_OVERLAP = _os.environ.get("UB_DDP_OVERLAP", "1") != "0"
+
+
 class GradSync:
     def __init__(self, arena=None, process_group=None):
         self.pg = process_group
@@ -37,7 +43,7 @@ class GradSync:
     # ---- overlapped form: called by backward as ranges become final ------------------------------
     def range_ready(self, flat: torch.Tensor, hi: int):
         """The decay-segment prefix [done, hi) of `flat` holds final gradients: reduce it now, asynchronously."""
-        if self.world == 1 or hi <= self._done_hi_decay:
+        if self.world == 1 or hi <= self._done_hi_decay or not _OVERLAP:
             return
         self._launch(flat[self._done_hi_decay:hi])
         self._done_hi_decay = hi
@@ -84,6 +90,17 @@ def init_distributed_from_env(backend: Optional[str] = None) -> Tuple[int, int, 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # SM partition between compute and the overlapped all-reduce: NCCL gets `reserve` CTAs (NCCL_MAX_CTAS), every persistent
+    # grid of the library is sized for the remaining SMs (ub_set_sm_limit).  Without it the collective's CTAs land on SMs a
+    # persistent GEMM assumed it owned and that GEMM's static schedule waits for them (measured: 17.21 -> 18.07 ms per step
+    # from 1 to 2 GPUs).  The experiment did not pay (see below); UB_DDP_RESERVED_SMS=n turns the partition on.
+    reserve = int(os.environ.get("UB_DDP_RESERVED_SMS", "0"))   # measured at 2 GPUs: 18.88 ms without, 19.11 (4) / 19.41 (8) with -> off
+    if world > 1 and reserve > 0 and torch.cuda.is_available():
+        os.environ.setdefault("NCCL_MAX_CTAS", str(reserve))
+        os.environ.setdefault("NCCL_MIN_CTAS", str(min(reserve, 4)))
+        from . import _cabi
+        _cabi.lib.ub_set_sm_limit(0)
+        _cabi.lib.ub_set_sm_limit(_cabi.lib.ub_sm_count() - reserve)
     if world > 1 and not dist.is_initialized():
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
