@@ -56,7 +56,16 @@ typedef struct ub_gemm_epilogue {
   int32_t tile_ctas;  /* scheduling hint: 0 = cost model, 1 / 2 / 4 = CTAs per work item (4 = two pairs + B multicast) */
   int32_t max_ctas;   /* scheduling hint: 0 = whole device, else cap on the persistent grid (a GEMM run beside another)  */
   int32_t residual_f16; /* 1: `residual` is fp16 [M, ldr] and C is fp16 too (out_fp32 must be 0): the teacher's residual stream */
-  int32_t reserved;
+  int32_t ab_f16;       /* 1: A and B hold fp16 (not bf16) values                                                          */
+  /* LayerNorm folded into the GEMM (frozen teacher): with A = the raw residual stream x (fp16), B = gamma o W, ln_c[n] =
+   * sum_k B[n,k] and bias = beta W^T + b, the result rstd_m * (acc - mu_m * ln_c[n]) + bias[n] equals Linear(LN(x)).
+   * ln_stats = fp32 [M,2] row (sum, sum of squares) of x, produced by the kernel that wrote x (stats_out below, or
+   * ub_teacher_embed_ln); mu = sum * ln_inv_d, var = sumsq * ln_inv_d - mu^2.  All three NULL / 0 when unused.            */
+  const float* ln_stats;
+  const float* ln_c;
+  float* stats_out;     /* residual_f16 epilogue only: += row (sum, sumsq) of the fp16 values written to C (must be zeroed)  */
+  float ln_inv_d;
+  float ln_eps;
 } ub_gemm_epilogue;
 
 /* a_mn_major / b_mn_major = 1: the operand is stored transposed, i.e. A is [K, lda>=M] / B is [K, ldb>=N]
@@ -100,9 +109,9 @@ UB_API int ub_cls_attn(const void* qkv, float* out, int n_seq, int S, int H, flo
 UB_API int ub_layernorm_fwd(const void* x, int x_f16, const int* src_rows, const float* gamma, const float* beta, float eps,
                             const float* post_add, const int* post_idx, void* out, int out_fp32, int rows, int D,
                             void* stream);
-/* out: fp32, or fp16 when out_f16 != 0 */
+/* out: fp32, or fp16 when out_f16 != 0; stats (may be NULL): fp32 [rows,2] = row (sum, sumsq) of the values written */
 UB_API int ub_teacher_embed_ln(const float* E, const float* cls, const float* pos, const float* gamma, const float* beta,
-                               float eps, void* out, int out_f16, int frames, int P, int D, void* stream);
+                               float eps, void* out, int out_f16, float* stats, int frames, int P, int D, void* stream);
 UB_API int ub_layernorm_bwd(const void* dy, const float* x, const float* gamma, float eps, const float* dx_in,
                             float* dx_out, void* dxs_out, const float* row_scale, int rows_per_scale, float* dgamma,
                             float* dbeta, float* dsum /* optional: += column sums of dxs (fp32) */, int rows, int D,

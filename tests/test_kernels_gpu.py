@@ -59,6 +59,15 @@ def test_gemm_all_operand_majors_and_epilogues():
     assert ok
 
 
+def test_gemm_layernorm_fold_and_fp16_residual_statistics():
+    """Teacher path: x = residual + A W^T written in fp16 with its row (sum, sumsq); the next GEMM consumes x directly and applies
+    LayerNorm in its epilogue (fp16 operands).  Against torch layer_norm + linear in fp32."""
+    g = importlib.import_module("gemm_check")
+    assert g.run_lnfold(1000, 2304, 768)
+    assert g.run_lnfold(2048, 3072, 768, act=1)
+    assert g.run_lnfold(300, 512, 256)
+
+
 @pytest.mark.parametrize("tub", [1, 2])
 def test_uint8_frames_to_normalised_patches_bit_exact(tub):
     """decoded uint8 frames [B,T,H,W,3] -> ToTensor + tensor_normalize + THWC->CTHW + patchify in one

@@ -91,3 +91,38 @@ if __name__ == "__main__":
     ok &= run(3072, 768, 10240, a_mn=1, b_mn=1, out_fp32=1, time_it=True)
     print("ALL OK" if ok else "SOME FAILED")
     sys.exit(0 if ok else 1)
+
+
+def run_lnfold(M, N, K, act=0):
+    """LayerNorm folded into the GEMM (fp16 operands) + fp16-residual epilogue producing the row statistics, vs torch."""
+    import torch.nn.functional as F
+    from unite_b200 import ops
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    x0 = (torch.randn(M, K, device=dev, generator=g) * 2 + 0.3)
+    r0 = torch.randn(M, K, device=dev, generator=g).half()
+    W0 = (torch.randn(K, K, device=dev, generator=g) * 0.03).bfloat16()
+    # producer: x = r0 + x0 @ W0^T in fp16 with row statistics
+    stats = torch.zeros(M, 2, device=dev)
+    x = torch.empty(M, K, device=dev, dtype=torch.float16)
+    ops.gemm(x0.bfloat16(), W0, x, residual=r0, stats_out=stats)
+    xf = x.float()
+    ok = True
+    e1 = (stats[:, 0] - xf.sum(1)).abs().max().item() / xf.sum(1).abs().max().item()
+    e2 = (stats[:, 1] - (xf * xf).sum(1)).abs().max().item() / (xf * xf).sum(1).abs().max().item()
+    ok &= e1 < 1e-5 and e2 < 1e-5
+    gamma = torch.rand(K, device=dev, generator=g) + 0.5
+    beta = torch.randn(K, device=dev, generator=g) * 0.1
+    W = torch.randn(N, K, device=dev, generator=g) * 0.05
+    b = torch.randn(N, device=dev, generator=g) * 0.1
+    ref = F.layer_norm(xf, (K,), gamma, beta, 1e-5) @ W.t() + b
+    if act == 1:
+        ref = ref * torch.sigmoid(1.702 * ref)
+    wg = (W * gamma[None, :]).half().contiguous()
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm(x, wg, out, bias=(W @ beta + b).contiguous(), act=act, ln_stats=stats, ln_c=wg.float().sum(1).contiguous(), ln_eps=1e-5)
+    torch.cuda.synchronize()
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    ok &= rel < 4e-3
+    print(f"LN-fold GEMM M={M} N={N} K={K} act={act}: stats err {e1:.1e}/{e2:.1e}, out rel {rel:.3e} {'OK' if ok else 'FAIL'}", flush=True)
+    return ok

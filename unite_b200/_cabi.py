@@ -29,7 +29,12 @@ class GemmEpilogue(C.Structure):
         ("tile_ctas", C.c_int32),
         ("max_ctas", C.c_int32),
         ("residual_f16", C.c_int32),
-        ("reserved", C.c_int32),
+        ("ab_f16", C.c_int32),
+        ("ln_stats", C.c_void_p),
+        ("ln_c", C.c_void_p),
+        ("stats_out", C.c_void_p),
+        ("ln_inv_d", C.c_float),
+        ("ln_eps", C.c_float),
     ]
 
 
@@ -57,7 +62,7 @@ SIGNATURES = {
     "ub_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "ub_cls_attn": (C.c_int, [_P, _P, _I, _I, _I, _F, _P]),
     "ub_layernorm_fwd": (C.c_int, [_P, _I, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P]),
-    "ub_teacher_embed_ln": (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _P]),
+    "ub_teacher_embed_ln": (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _I, _P, _I, _I, _I, _P]),
     "ub_layernorm_bwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P]),
     "ub_dec_tail_fwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _F, _I, _I, _P]),
     "ub_dec_tail_bwd": (C.c_int, [_P, _P, _P, _F, _P, _F, _P, _P, _P, _I, _I, _P]),

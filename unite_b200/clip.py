@@ -28,6 +28,11 @@ BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
 # UB_TEACHER_STREAM=fp32 restores the fp32 stream.
 import os as _os
 STREAM = F32 if _os.environ.get("UB_TEACHER_STREAM", "fp16") == "fp32" else torch.float16
+# ln_1 / ln_2 folded into the QKV / c_fc GEMMs (needs the fp16 stream): the GEMM reads the raw residual stream x as its fp16 A
+# operand against B = fp16(gamma o W); its epilogue applies rstd_m * (acc - mu_m * c_n) + (beta W^T + b)_n with the row
+# statistics the producer of x accumulated in ITS epilogue.  Algebraically identical to Linear(LayerNorm(x)); 24 LayerNorm
+# launches and their 154 MB each disappear, and the operands carry 11 instead of 8 mantissa bits.  UB_TEACHER_LNFOLD=0: off.
+LNFOLD = STREAM == torch.float16 and _os.environ.get("UB_TEACHER_LNFOLD", "1") != "0"
 
 
 class LayerNorm(nn.LayerNorm):
@@ -102,6 +107,14 @@ class VisionTransformer(nn.Module):
                 w[f"{i}.out_proj"] = blk.attn.out_proj.weight.detach().to(BF16).contiguous()
                 w[f"{i}.c_fc"] = blk.mlp.c_fc.weight.detach().to(BF16).contiguous()
                 w[f"{i}.c_proj"] = blk.mlp.c_proj.weight.detach().to(BF16).contiguous()
+                if LNFOLD:
+                    for name, ln, lin_w, lin_b in ((f"{i}.in_proj", blk.ln_1, blk.attn.in_proj_weight, blk.attn.in_proj_bias),
+                                                   (f"{i}.c_fc", blk.ln_2, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias)):
+                        Wf = lin_w.detach().float()
+                        wg = (Wf * ln.weight.detach().float()[None, :]).to(torch.float16).contiguous()      # gamma o W
+                        w[name + ".fold"] = wg
+                        w[name + ".fold_c"] = wg.float().sum(dim=1).contiguous()                            # c_n = sum_k B[n,k]
+                        w[name + ".fold_d"] = (Wf @ ln.bias.detach().float() + lin_b.detach().float()).contiguous()
             self._w16, self._w_version = w, v
         return self._w16
 
@@ -114,6 +127,7 @@ class VisionTransformer(nn.Module):
             self._bufs[key] = dict(
                 E=torch.empty(frames * P, W, device=dev, dtype=F32),
                 x=[torch.empty(R, W, device=dev, dtype=STREAM) for _ in range(K + 2)],   # work, mid, K snapshots
+                stats=torch.zeros(2 * len(self.transformer.resblocks), R, 2, device=dev, dtype=F32),   # LN fold: row (sum, sumsq)
                 h=torch.empty(R, W, device=dev, dtype=BF16), qkv=torch.empty(R, 3 * W, device=dev, dtype=BF16),
                 o=torch.empty(R, W, device=dev, dtype=BF16), u=torch.empty(R, 4 * W, device=dev, dtype=BF16))
         return self._bufs[key]
@@ -142,8 +156,11 @@ class VisionTransformer(nn.Module):
         xs = bufs["x"]
         work, mid, snaps = xs[0], xs[1], xs[2:]
         cur = work
+        stats = bufs["stats"] if LNFOLD else None
+        if LNFOLD:
+            stats.zero_()
         ops.teacher_embed_ln(bufs["E"], self.class_embedding.detach(), self.positional_embedding.detach(), self.ln_pre.weight.detach(),
-                             self.ln_pre.bias.detach(), self.ln_pre.eps, cur, frames, P, W)
+                             self.ln_pre.bias.detach(), self.ln_pre.eps, cur, frames, P, W, stats=stats[0] if LNFOLD else None)
         keep: List[torch.Tensor] = []
         attn = None
         ret = self.transformer.return_index
@@ -151,8 +168,12 @@ class VisionTransformer(nn.Module):
         scale = 64 ** -0.5
         self.last_gathered = False
         for i, blk in enumerate(self.transformer.resblocks):
-            ops.layernorm_fwd(cur, blk.ln_1.weight.detach(), blk.ln_1.bias.detach(), blk.ln_1.eps, bufs["h"])
-            ops.gemm(bufs["h"], w[f"{i}.in_proj"], bufs["qkv"], bias=blk.attn.in_proj_bias.detach())
+            if LNFOLD:
+                ops.gemm(cur, w[f"{i}.in_proj.fold"], bufs["qkv"], bias=w[f"{i}.in_proj.fold_d"], ln_stats=stats[2 * i],
+                         ln_c=w[f"{i}.in_proj.fold_c"], ln_eps=blk.ln_1.eps)
+            else:
+                ops.layernorm_fwd(cur, blk.ln_1.weight.detach(), blk.ln_1.bias.detach(), blk.ln_1.eps, bufs["h"])
+                ops.gemm(bufs["h"], w[f"{i}.in_proj"], bufs["qkv"], bias=blk.attn.in_proj_bias.detach())
             if i == nblk - 1 and self.return_attn:
                 attn = torch.empty(frames, P, device=x.device, dtype=F32)
                 ops.cls_attn(bufs["qkv"], attn, frames, S, self.heads, scale)
@@ -163,20 +184,33 @@ class VisionTransformer(nn.Module):
                 tb = self._tail_buffers(n)
                 ops.gather_rows(bufs["o"], rows, tb["o"])
                 ops.gather_rows(cur, rows, tb["x"])
-                ops.gemm(tb["o"], w[f"{i}.out_proj"], tb["mid"], bias=blk.attn.out_proj.bias.detach(), residual=tb["x"])
-                ops.layernorm_fwd(tb["mid"], blk.ln_2.weight.detach(), blk.ln_2.bias.detach(), blk.ln_2.eps, tb["h"])
-                ops.gemm(tb["h"], w[f"{i}.c_fc"], tb["u"], bias=blk.mlp.c_fc.bias.detach(), act=ops.UB_ACT_QUICKGELU)
+                if LNFOLD:
+                    tb["stats"].zero_()
+                    ops.gemm(tb["o"], w[f"{i}.out_proj"], tb["mid"], bias=blk.attn.out_proj.bias.detach(), residual=tb["x"],
+                             stats_out=tb["stats"])
+                    ops.gemm(tb["mid"], w[f"{i}.c_fc.fold"], tb["u"], bias=w[f"{i}.c_fc.fold_d"], act=ops.UB_ACT_QUICKGELU,
+                             ln_stats=tb["stats"], ln_c=w[f"{i}.c_fc.fold_c"], ln_eps=blk.ln_2.eps)
+                else:
+                    ops.gemm(tb["o"], w[f"{i}.out_proj"], tb["mid"], bias=blk.attn.out_proj.bias.detach(), residual=tb["x"])
+                    ops.layernorm_fwd(tb["mid"], blk.ln_2.weight.detach(), blk.ln_2.bias.detach(), blk.ln_2.eps, tb["h"])
+                    ops.gemm(tb["h"], w[f"{i}.c_fc"], tb["u"], bias=blk.mlp.c_fc.bias.detach(), act=ops.UB_ACT_QUICKGELU)
                 ops.gemm(tb["u"], w[f"{i}.c_proj"], tb["out"], bias=blk.mlp.c_proj.bias.detach(), residual=tb["mid"])
                 keep.append(tb["out"])
                 self.last_gathered = True
                 self.last_stream = None
                 return keep, attn, patches
-            ops.gemm(bufs["o"], w[f"{i}.out_proj"], mid, bias=blk.attn.out_proj.bias.detach(), residual=cur)
-            ops.layernorm_fwd(mid, blk.ln_2.weight.detach(), blk.ln_2.bias.detach(), blk.ln_2.eps, bufs["h"])
-            ops.gemm(bufs["h"], w[f"{i}.c_fc"], bufs["u"], bias=blk.mlp.c_fc.bias.detach(), act=ops.UB_ACT_QUICKGELU)
+            if LNFOLD:
+                ops.gemm(bufs["o"], w[f"{i}.out_proj"], mid, bias=blk.attn.out_proj.bias.detach(), residual=cur, stats_out=stats[2 * i + 1])
+                ops.gemm(mid, w[f"{i}.c_fc.fold"], bufs["u"], bias=w[f"{i}.c_fc.fold_d"], act=ops.UB_ACT_QUICKGELU,
+                         ln_stats=stats[2 * i + 1], ln_c=w[f"{i}.c_fc.fold_c"], ln_eps=blk.ln_2.eps)
+            else:
+                ops.gemm(bufs["o"], w[f"{i}.out_proj"], mid, bias=blk.attn.out_proj.bias.detach(), residual=cur)
+                ops.layernorm_fwd(mid, blk.ln_2.weight.detach(), blk.ln_2.bias.detach(), blk.ln_2.eps, bufs["h"])
+                ops.gemm(bufs["h"], w[f"{i}.c_fc"], bufs["u"], bias=blk.mlp.c_fc.bias.detach(), act=ops.UB_ACT_QUICKGELU)
             # a returned layer gets its own snapshot buffer (never written again); others go to the work buffer
             dst = snaps[len(keep)] if i in ret else work
-            ops.gemm(bufs["u"], w[f"{i}.c_proj"], dst, bias=blk.mlp.c_proj.bias.detach(), residual=mid)
+            ops.gemm(bufs["u"], w[f"{i}.c_proj"], dst, bias=blk.mlp.c_proj.bias.detach(), residual=mid,
+                     stats_out=stats[2 * i + 2] if (LNFOLD and i + 1 < nblk) else None)
             cur = dst
             if i in ret:
                 keep.append(cur)
@@ -189,7 +223,8 @@ class VisionTransformer(nn.Module):
             dev, W = self.proj.device, self.width
             self._bufs[key] = dict(o=torch.empty(n, W, device=dev, dtype=BF16), x=torch.empty(n, W, device=dev, dtype=STREAM),
                                    mid=torch.empty(n, W, device=dev, dtype=STREAM), h=torch.empty(n, W, device=dev, dtype=BF16),
-                                   u=torch.empty(n, 4 * W, device=dev, dtype=BF16), out=torch.empty(n, W, device=dev, dtype=STREAM))
+                                   u=torch.empty(n, 4 * W, device=dev, dtype=BF16), out=torch.empty(n, W, device=dev, dtype=STREAM),
+                                   stats=torch.zeros(n, 2, device=dev, dtype=F32))
         return self._bufs[key]
 
     @torch.no_grad()

@@ -41,6 +41,11 @@ struct GemmParams {
   int act;
   int accumulate;
   int has_aux_out;
+  int ab_f16;               // operands are fp16 instead of bf16
+  const float* ln_stats;    // LayerNorm fold: row (sum, sumsq) of A
+  const float* ln_c;        //                 column sums of B
+  float ln_inv_d, ln_eps;
+  float* stats_out;         // EPI 3: row (sum, sumsq) of the fp16 output
 };
 
 // EPI : 0 = bias / activation (/ pre-activation copy), 1 = + fp32 residual (fp32 out), 2 = DGELU: * gelu'(aux) (bf16 out),
@@ -61,7 +66,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int B_BYTES = BN_L * BK * 2;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // 256 or 512: power of two
-  constexpr uint32_t IDESC = umma_idesc_bf16(BM * CG, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  constexpr uint32_t IDESC_BF16 = umma_idesc_bf16(BM * CG, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  constexpr uint32_t FMT_BF16 = (1u << 7) | (1u << 10);          // a_format / b_format = BF16; 0 = F16
+  const uint32_t IDESC = p.ab_f16 ? (IDESC_BF16 & ~FMT_BF16) : IDESC_BF16;
   constexpr int CW = OUT32 ? 32 : 64;        // columns per epilogue slab
   constexpr int SLABS = (BN / 2) / CW;       // slabs per warp per tile
   static_assert(EPI != 1 || OUT32, "residual epilogue writes fp32");
@@ -262,6 +269,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int row = row0 + lane;
         rscale = row < p.M ? __ldg(p.row_scale + row / p.rows_per_scale) : 0.0f;
       }
+      float ln_rstd = 1.0f, ln_rm = 0.0f;       // LayerNorm fold: acc -> rstd * acc - (rstd * mu) * c[n]
+      if (EPI == 0 && p.ln_stats != nullptr) {
+        const int row = row0 + lane;
+        if (row < p.M) {
+          const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + row);
+          const float mu = st.x * p.ln_inv_d;
+          ln_rstd = rsqrtf(fmaxf(st.y * p.ln_inv_d - mu * mu, 0.0f) + p.ln_eps);
+          ln_rm = ln_rstd * mu;
+        }
+      }
+      float st1 = 0.0f, st2 = 0.0f;             // EPI 3: row statistics of the fp16 values this thread writes
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(sp * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
@@ -295,10 +313,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int h = 0; h < CW / 32; ++h) {
           uint32_t r[32];
           tmem_ld_32x32(t_row + (uint32_t)(c * CW + h * 32), r);
+          // LayerNorm fold: the column sums of B for these 32 columns are fetched (L1-resident, same address for every lane)
+          // while the accumulator load is in flight
+          float4 cc[EPI == 0 ? 8 : 1];
+          if (EPI == 0 && p.ln_stats != nullptr) {
+            const int gc = col0 + h * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              cc[EPI == 0 ? j : 0] = (gc + 4 * j < p.N) ? __ldg(reinterpret_cast<const float4*>(p.ln_c + gc + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (EPI == 0 && p.ln_stats != nullptr) {
+            const float2 rs2 = make_float2(ln_rstd, ln_rstd), nrm2 = make_float2(-ln_rm, -ln_rm);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 q = cc[EPI == 0 ? j : 0];
+              const float2 a = __ffma2_rn(nrm2, make_float2(q.x, q.y), __fmul2_rn(rs2, make_float2(v[4 * j], v[4 * j + 1])));
+              const float2 b = __ffma2_rn(nrm2, make_float2(q.z, q.w), __fmul2_rn(rs2, make_float2(v[4 * j + 2], v[4 * j + 3])));
+              v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = b.x; v[4 * j + 3] = b.y;
+            }
+          }
           if (p.bias != nullptr) {
             const float* bt = bias_tile + half * (BN / 2) + c * CW + h * 32;
 #pragma unroll
@@ -375,6 +412,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&pk.z)), r3 = __half22float2(*reinterpret_cast<const __half2*>(&pk.w));
               const __half2 o0 = __floats2half2_rn(v[8 * j] + r0.x, v[8 * j + 1] + r0.y), o1 = __floats2half2_rn(v[8 * j + 2] + r1.x, v[8 * j + 3] + r1.y);
               const __half2 o2 = __floats2half2_rn(v[8 * j + 4] + r2.x, v[8 * j + 5] + r2.y), o3 = __floats2half2_rn(v[8 * j + 6] + r3.x, v[8 * j + 7] + r3.y);
+              if (p.stats_out != nullptr) {
+                const float2 f0 = __half22float2(o0), f1 = __half22float2(o1), f2 = __half22float2(o2), f3 = __half22float2(o3);
+                st1 += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+                st2 += ((f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y)) + ((f2.x * f2.x + f2.y * f2.y) + (f3.x * f3.x + f3.y * f3.y));
+              }
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(*reinterpret_cast<const uint32_t*>(&o0)),
                            "r"(*reinterpret_cast<const uint32_t*>(&o1)), "r"(*reinterpret_cast<const uint32_t*>(&o2)),
                            "r"(*reinterpret_cast<const uint32_t*>(&o3))
@@ -400,6 +442,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (EPI == 0 && p.has_aux_out) tma_store_2d(&tmX, slab0 + ((b ^ 1) << 12), col0, row0);
           tma_store_commit();
         }
+      }
+      if (EPI == 3 && p.stats_out != nullptr && row0 + lane < p.M) {
+        atomicAdd(p.stats_out + 2 * (size_t)(row0 + lane), st1);
+        atomicAdd(p.stats_out + 2 * (size_t)(row0 + lane) + 1, st2);
       }
       tc_fence_before();
       __syncwarp();
@@ -590,6 +636,10 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   UB_REQUIRE(!(ep.act == UB_ACT_DGELU && ep.residual != nullptr), "gemm: DGELU with a residual is not supported");
   UB_REQUIRE(ep.residual == nullptr || ep.out_fp32 || ep.residual_f16, "gemm: the residual epilogue writes fp32 (or fp16 with residual_f16)");
   UB_REQUIRE(!ep.residual_f16 || (ep.residual != nullptr && !ep.out_fp32), "gemm: residual_f16 needs a residual and a 2-byte (fp16) output");
+  UB_REQUIRE((ep.ln_stats == nullptr) == (ep.ln_c == nullptr), "gemm: ln_stats and ln_c go together");
+  UB_REQUIRE(ep.ln_stats == nullptr || (ep.residual == nullptr && ep.act != UB_ACT_DGELU && !ep.accumulate && ep.ln_inv_d > 0.f && N % 4 == 0),
+             "gemm: the LayerNorm fold works with the bias / activation epilogue only");
+  UB_REQUIRE(ep.stats_out == nullptr || ep.residual_f16, "gemm: stats_out belongs to the fp16-residual epilogue");
   UB_REQUIRE(ep.act != UB_ACT_DGELU || !ep.out_fp32, "gemm: the DGELU epilogue writes bf16");
   UB_REQUIRE(ep.residual == nullptr || (ep.act == UB_ACT_NONE && !ep.accumulate),
              "gemm: residual cannot be combined with an activation / accumulate");
@@ -666,6 +716,9 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   p.splits = split_k; p.kb_per_split = kb_per_split;
   p.bias = ep.bias; p.row_scale = ep.row_scale; p.rows_per_scale = ep.rows_per_scale;
   p.act = ep.act; p.accumulate = ep.accumulate; p.has_aux_out = ep.aux_out != nullptr;
+  p.ab_f16 = ep.ab_f16;
+  p.ln_stats = ep.ln_stats; p.ln_c = ep.ln_c; p.ln_inv_d = ep.ln_inv_d; p.ln_eps = ep.ln_eps;
+  p.stats_out = ep.stats_out;
   const long total_work = (long)((M + BM * ncta - 1) / (BM * ncta)) * ((N + bn - 1) / bn) * split_k;
   int units = ncta == 4 ? units4 : sms / ncta;
   if (ep.max_ctas > 0 && ep.max_ctas / ncta >= 1 && ep.max_ctas / ncta < units) units = ep.max_ctas / ncta;

@@ -168,7 +168,8 @@ template <int NV>
 __global__ void __launch_bounds__(256) teacher_embed_ln_kernel(const float* __restrict__ E, const float* __restrict__ cls,
                                                                const float* __restrict__ pos, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, void* __restrict__ out,
-                                                               int frames, int P, int D, float eps, int out_f16) {
+                                                               int frames, int P, int D, float eps, int out_f16,
+                                                               float* __restrict__ stats) {
   pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   constexpr int nv = NV;
@@ -195,6 +196,20 @@ __global__ void __launch_bounds__(256) teacher_embed_ln_kernel(const float* __re
     }
     if (out_f16) row_store_f16(x, reinterpret_cast<__half*>(out) + (int64_t)row * D, nv, lane);
     else row_store_f32(x, reinterpret_cast<float*>(out) + (int64_t)row * D, nv, lane);
+    if (stats != nullptr) {
+      // row (sum, sum of squares) of the values as STORED: the next GEMM folds the following LayerNorm into its epilogue
+      if (out_f16) {
+        UB_ROW_FOREACH(i, nv) {
+          x.v[i].x = __half2float(__float2half_rn(x.v[i].x)); x.v[i].y = __half2float(__float2half_rn(x.v[i].y));
+          x.v[i].z = __half2float(__float2half_rn(x.v[i].z)); x.v[i].w = __half2float(__float2half_rn(x.v[i].w));
+        }
+      }
+      const float s1 = row_sum(x, nv), s2 = row_dot(x, x, nv);
+      if (lane == 0) {
+        stats[2 * (int64_t)row] = s1;
+        stats[2 * (int64_t)row + 1] = s2;
+      }
+    }
   }
 }
 
@@ -457,10 +472,11 @@ extern "C" int ub_layernorm_fwd(const void* x, int x_f16, const int* src_rows, c
 }
 
 extern "C" int ub_teacher_embed_ln(const float* E, const float* cls, const float* pos, const float* gamma,
-                                   const float* beta, float eps, void* out, int out_f16, int frames, int P, int D, void* stream) {
+                                   const float* beta, float eps, void* out, int out_f16, float* stats, int frames, int P, int D,
+                                   void* stream) {
   UB_REQUIRE(E && cls && pos && gamma && beta && out, "teacher_embed_ln: null pointer");
   if (check_D(D, "teacher_embed_ln")) return 1;
-  UB_LN_DISPATCH(D, teacher_embed_ln_kernel, ln_grid(frames * (P + 1)), 0, (cudaStream_t)stream, E, cls, pos, gamma, beta, out, frames, P, D, eps, out_f16)
+  UB_LN_DISPATCH(D, teacher_embed_ln_kernel, ln_grid(frames * (P + 1)), 0, (cudaStream_t)stream, E, cls, pos, gamma, beta, out, frames, P, D, eps, out_f16, stats)
   return check_launch("teacher_embed_ln_kernel");
 }
 

@@ -70,10 +70,13 @@ def _p2d(t: torch.Tensor, dtype, what):
 @_instrument("gemm", 1)
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=False, bias=None, residual=None,
          row_scale=None, rows_per_scale=0, act=UB_ACT_NONE, aux_in=None, aux_out=None, accumulate=False, split_k=1, tile_ctas=0,
-         max_ctas=0):
-    """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).  a_t / b_t: the operand is stored transposed ([K,M] / [K,N])."""
-    pa, lda = _p2d(a, BF16, "gemm A")
-    pb, ldb = _p2d(b, BF16, "gemm B")
+         max_ctas=0, ln_stats=None, ln_c=None, ln_eps=0.0, stats_out=None):
+    """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).  a_t / b_t: the operand is stored transposed ([K,M] / [K,N]).
+    A and B are both bf16 or both fp16.  ln_stats / ln_c: LayerNorm of A's rows folded into the epilogue (see the header);
+    stats_out: row (sum, sumsq) of an fp16-residual output, accumulated."""
+    ab = F16 if a.dtype == F16 else BF16
+    pa, lda = _p2d(a, ab, "gemm A")
+    pb, ldb = _p2d(b, ab, "gemm B")
     if out.dtype not in (BF16, F32, F16):
         raise _cabi.UBError("gemm out: bf16, fp32 or (with an fp16 residual) fp16 expected")
     if out.dtype == F16 and (residual is None or residual.dtype != F16):
@@ -112,6 +115,16 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=
     ep.out_fp32 = 1 if out.dtype == F32 else 0
     ep.accumulate = 1 if accumulate else 0
     ep.tile_ctas, ep.max_ctas = tile_ctas, max_ctas
+    ep.ab_f16 = 1 if ab == F16 else 0
+    if ln_stats is not None:
+        if ln_c is None or ln_c.numel() != N or tuple(ln_stats.shape) != (M, 2):
+            raise _cabi.UBError("gemm: ln_stats must be fp32 [M,2] and ln_c fp32 [N]")
+        ep.ln_stats, ep.ln_c = _p(ln_stats, F32, "ln_stats"), _p(ln_c, F32, "ln_c")
+        ep.ln_inv_d, ep.ln_eps = 1.0 / K, ln_eps
+    if stats_out is not None:
+        if tuple(stats_out.shape) != (M, 2):
+            raise _cabi.UBError("gemm: stats_out must be fp32 [M,2]")
+        ep.stats_out = _p(stats_out, F32, "stats_out")
     check(lib.ub_gemm_bf16(pa, lda, int(a_t), pb, ldb, int(b_t), pc, ldc, M, N, K, C.byref(ep), split_k, _stream()), "ub_gemm_bf16")
     return out
 
@@ -144,9 +157,10 @@ def layernorm_fwd(x, gamma, beta, eps, out, *, src_rows=None, post_add=None, pos
 
 
 @_instrument("teacher_embed_ln", 1)
-def teacher_embed_ln(E, cls, pos, gamma, beta, eps, out, frames, P, D):
+def teacher_embed_ln(E, cls, pos, gamma, beta, eps, out, frames, P, D, stats=None):
     check(lib.ub_teacher_embed_ln(_p(E, F32, "E"), _p(cls, F32, "cls"), _p(pos, F32, "pos"), _p(gamma, F32, "gamma"),
-                                  _p(beta, F32, "beta"), eps, _p(out, None, "out"), 1 if out.dtype == F16 else 0, frames, P, D, _stream()),
+                                  _p(beta, F32, "beta"), eps, _p(out, None, "out"), 1 if out.dtype == F16 else 0,
+                                  _p(stats, F32, "stats"), frames, P, D, _stream()),
           "ub_teacher_embed_ln")
 
 
