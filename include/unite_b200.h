@@ -163,6 +163,32 @@ UB_API int ub_adamw_dev(float* p, const float* g, float* m, float* v, void* w_bf
 UB_API int ub_cast_bf16(const float* x, void* out, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Data-parallel optimizer step fused with its collective (replaces DistributedDataParallel's bucketed all-reduce,
+ * run_stage1.py:809 / run_stage2.py:641 / run_stage3.py:1246, + utils.py:608-622 + optim_factory.py:162-163):
+ * reduce-scatter of the gradient arena inside the NVSwitch (multimem.ld_reduce), AdamW on the rank's slice of the decay
+ * segment, all-gather of the refreshed bf16 shadow (multimem.st) — one kernel, no NCCL call.  `g_mc`, `w16_mc`,
+ * `gnorm_sq_mc`, `flags_mc` are MULTICAST addresses of symmetric allocations (same size and offset on every rank);
+ * `w16`, `flags` the rank's own mappings of the same memory.  p / m / v are local; their decay segment is updated on the
+ * owning rank only (ZeRO-1), the no-decay segment on every rank.  flags: ub_nvls_slots() zero-initialised uint32 (symmetric),
+ * epoch: ub_nvls_slots()/2 zero-initialised uint32 (local), err: one int32 (local; 1 / 2 = a peer never reached the entry /
+ * exit barrier within ~30 s — the kernel then finishes instead of hanging).  hyper[8] as for ub_adamw_dev with
+ * grad_scale = 1/world.  Every rank must launch it the same number of times.
+ * g_peers / w16_peers (host arrays of `world` device pointers, by rank: every rank's mapping of the gradient arena / shadow,
+ * own rank included): when given and world is 2, 4 or 8 the gradients are read with plain NVLink peer loads and summed in
+ * rank order (bitwise reproducible) and the shadow is written with one store per peer, instead of multimem.ld_reduce /
+ * multimem.st; the barriers and the gradient norm always use the multicast mapping.
+ * stage_peers (every rank's mapping of a symmetric staging buffer of world * ceil(n_decay/8/world) * 8 floats): selects the
+ * PUSH form — each rank first writes its gradients of every peer's slice into slot[rank] of that peer's staging buffer
+ * (posted NVLink writes), a grid-wide cross-GPU counter follows, then the owner sums local copies in rank order.
+ * ---------------------------------------------------------------------------------------------- */
+UB_API int ub_nvls_slots(void);
+UB_API int ub_adamw_nvls(float* p, const float* g_mc, float* m, float* v, void* w16, void* w16_mc, int64_t n, int64_t n_decay,
+                         int rank, int world, const float* hyper, float* gnorm_sq_mc /* may be NULL */, uint32_t* flags,
+                         uint32_t* flags_mc, uint32_t* epoch, int32_t* err, const void* const* g_peers /* host array [world] or NULL */,
+                         void* const* w16_peers /* host array [world] or NULL */,
+                         void* const* stage_peers /* host array [world] or NULL */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Classification heads and stage-3 pseudo-label fusion (fp32, small).
  *   ub_meanpool_fwd/bwd      x.mean(1): modeling_finetune.py:374-376 (stage 2), run_stage3.py:333-338 pool_outputs
  *   ub_linear_small_fwd/bwd  few-output Linear: `head` (modeling_finetune.py:382), `src_classifier` (run_stage3.py:1193);

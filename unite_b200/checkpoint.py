@@ -168,6 +168,8 @@ def _is_master() -> bool:
 def save_model(output_dir: str, epoch, model_without_ddp, optimizer, loss_scaler=None, args=None, tag: Optional[str] = None) -> str:
     """`checkpoint-<epoch or tag>.pth` = {model, optimizer, epoch, scaler, args}; written by rank 0 only."""
     path = os.path.join(output_dir, "checkpoint-%s.pth" % (tag if tag is not None else str(epoch)))
+    if hasattr(optimizer, "consolidate"):
+        optimizer.consolidate()        # collective: gathers the rank-sharded fp32 master weights / Adam moments (ddp.NvlsShardedStep)
     if _is_master():
         os.makedirs(output_dir, exist_ok=True)
         to_save = {"model": model_without_ddp.state_dict(), "optimizer": optimizer.state_dict(), "epoch": epoch, "args": args,

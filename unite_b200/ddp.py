@@ -71,6 +71,94 @@ class GradSync:
             torch.cuda.current_stream().wait_stream(self._stream)
 
 
+class NvlsShardedStep:
+    """Gradient reduce-scatter + AdamW + bf16-shadow all-gather in ONE kernel over NVSwitch multicast (csrc/ddp_nvls.cu),
+    instead of NCCL all-reduce -> AdamW.  The gradient arena and the bf16 shadow are re-homed into symmetric memory
+    (torch.distributed._symmetric_memory: one VMM allocation per rank bound to a multicast object); the kernel reads the
+    SUM of all ranks' gradients with multimem.ld_reduce and writes the refreshed shadow to all ranks with multimem.st.
+    fp32 master weights / Adam moments of the decay segment are sharded by rank (ZeRO-1): call consolidate() before
+    reading them (state_dict, checkpoint); the no-decay segment and the bf16 shadow are always replicated.
+
+    Raises RuntimeError when the box has no multicast support; the caller then stays on the NCCL path (GradSync)."""
+
+    def __init__(self, arena, optimizer, process_group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _cabi
+        self.arena, self.opt = arena, optimizer
+        self.pg = process_group if process_group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.pg), dist.get_world_size(self.pg)
+        dev, n = arena.device, arena.numel
+        if n % 8 or arena.n_decay % 8:
+            raise RuntimeError("arena size / decay boundary must be multiples of 8 elements")
+        slots = int(_cabi.lib.ub_nvls_slots())
+        self._grads = symm.empty(n, dtype=torch.float32, device=dev)
+        self._w16 = symm.empty(n, dtype=torch.bfloat16, device=dev)
+        self._sync = symm.empty(slots + 8, dtype=torch.int32, device=dev)     # [gnorm_sq f32 | 7 pad | flags u32[slots]]
+        # push form: slot s of my staging buffer receives rank s's gradients of MY slice of the decay segment
+        lo, hi = self.shard_of(arena.n_decay, 0, self.world)
+        self._stage = symm.empty(max(8, self.world * (hi - lo)), dtype=torch.float32, device=dev)
+        self._hdl = [symm.rendezvous(t, self.pg) for t in (self._grads, self._w16, self._sync, self._stage)]
+        if any(int(h.multicast_ptr) == 0 for h in self._hdl[:3]):
+            raise RuntimeError("symmetric memory has no multicast mapping on this box (NVLS unavailable)")
+        self._grads.copy_(arena.grads)
+        self._w16.copy_(arena.w16)
+        self._sync.zero_()
+        arena.grads, arena.w16 = self._grads, self._w16          # p.grad views are re-pointed by arena.attach_grads()
+        for p in arena._params.values():
+            p.grad = None
+        optimizer.gnorm_sq = self._sync[:1].view(torch.float32)
+        optimizer._sharded = self                                  # FusedAdamW.consolidate() / checkpoint.save_model() find it here
+        self._epoch = torch.zeros(slots // 2, device=dev, dtype=torch.int32)
+        self._err = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.g_mc, self.w16_mc, sync_mc = (int(h.multicast_ptr) for h in self._hdl[:3])
+        self.gnorm_mc, self.flags_mc = sync_mc, sync_mc + 32
+        import ctypes
+        self.g_peers = (ctypes.c_void_p * self.world)(*[int(a) for a in self._hdl[0].buffer_ptrs])
+        self.w16_peers = (ctypes.c_void_p * self.world)(*[int(a) for a in self._hdl[1].buffer_ptrs])
+        self.stage_peers = (ctypes.c_void_p * self.world)(*[int(a) for a in self._hdl[3].buffer_ptrs])
+        self.flags = self._sync.data_ptr() + 32
+        self.calls = 0
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.pg)                                      # every rank's buffers are initialised before anyone's kernel
+        torch.cuda.synchronize(dev)
+
+    @staticmethod
+    def shard_of(n_decay: int, rank: int, world: int) -> Tuple[int, int]:
+        """[lo, hi) elements of the decay segment owned by `rank`: contiguous slices of ceil(n_decay/8 / world) 8-element
+        units (the arithmetic of adamw_nvls_kernel)."""
+        n8 = n_decay // 8
+        shard = (n8 + world - 1) // world
+        lo = min(rank * shard, n8)
+        return lo * 8, min(lo + shard, n8) * 8
+
+    def shard_range(self, rank=None):
+        return self.shard_of(self.arena.n_decay, self.rank if rank is None else rank, self.world)
+
+    def step_dev(self):
+        """Device side of the step (graph-capturable); the optimizer's prepare_step() uploaded hyper[] with grad_scale = 1/world."""
+        from . import ops
+        a, o = self.arena, self.opt
+        o.gnorm_sq.zero_()
+        ops.adamw_nvls(a.params, self.g_mc, o.exp_avg, o.exp_avg_sq, a.w16, self.w16_mc, a.n_decay, self.rank, self.world,
+                       o._hyper_dev, self.gnorm_mc, self.flags, self.flags_mc, self._epoch, self._err, self.g_peers, self.w16_peers, self.stage_peers)
+        self.calls += 1
+
+    def check(self):
+        """Host-side health check (syncs): raises if a peer ever missed a barrier inside the kernel."""
+        code = int(self._err.item())
+        if code:
+            raise RuntimeError(f"ub_adamw_nvls: a peer never reached the {'entry' if code == 1 else 'exit'} barrier (rank {self.rank})")
+
+    def consolidate(self):
+        """Gather the sharded fp32 master weights and Adam moments so that every rank holds all of them."""
+        self.check()
+        for r in range(self.world):
+            lo, hi = self.shard_range(r)
+            if hi > lo:
+                for t in (self.arena.params, self.opt.exp_avg, self.opt.exp_avg_sq):
+                    dist.broadcast(t[lo:hi], src=dist.get_global_rank(self.pg, r), group=self.pg)
+
+
 class DataParallel(torch.nn.Module):
     """Thin wrapper with DDP's surface (`.module`, forward passthrough); gradient averaging is done by GradSync
     inside the engines, not by autograd hooks."""

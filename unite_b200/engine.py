@@ -12,6 +12,7 @@ src_classifier=None:
 Nothing in the step reads a device value on the host: the loss and grad-norm stay on the GPU until the caller asks.
 """
 import math
+import os
 from typing import Optional
 
 import torch
@@ -71,6 +72,13 @@ class FusedAdamW:
         ops.adamw(a.params, a.grads, self.exp_avg, self.exp_avg_sq, a.w16, a.n_decay, g0["lr"], g0["weight_decay"], self.betas[0],
                   self.betas[1], self.eps, self.step_count, grad_scale)
 
+    def consolidate(self):
+        """Collective no-op unless the optimizer state is sharded by rank (ddp.NvlsShardedStep attaches itself as `_sharded`):
+        afterwards every rank holds all fp32 master weights and Adam moments.  Call it on EVERY rank before state_dict()."""
+        sharded = getattr(self, "_sharded", None)
+        if sharded is not None:
+            sharded.consolidate()
+
     def grad_norm(self, grad_scale: float = 1.0) -> torch.Tensor:
         return self.gnorm_sq.sqrt() * grad_scale
 
@@ -100,6 +108,19 @@ class Stage1Engine:
         self.core.sync_shadow(force=True)
         self.optimizer = FusedAdamW(self.core.arena, lr, weight_decay, betas, eps)
         self.grad_sync = grad_sync            # unite_b200.ddp.GradSync or None
+        # N > 1: the all-reduce -> AdamW pair becomes ONE kernel over NVSwitch multicast (ddp.NvlsShardedStep) when the box
+        # offers it; UB_DDP_NVLS=0 (or a box without multicast) keeps NCCL range all-reduces overlapped with backward
+        self.nvls = None
+        if grad_sync is not None and getattr(grad_sync, "world", 1) > 1 and self.core.arena.device.type == "cuda" \
+                and os.environ.get("UB_DDP_NVLS", "1") != "0":
+            from .ddp import NvlsShardedStep
+            try:
+                self.nvls = NvlsShardedStep(self.core.arena, self.optimizer, grad_sync.pg)
+            except Exception as e:                      # no multicast / symmetric memory on this box: NCCL path
+                if os.environ.get("UB_DDP_NVLS") == "1":
+                    raise
+                import warnings
+                warnings.warn(f"unite_b200: NVLS fused optimizer step unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
         self.share_patches = student.encoder.patch_embed.tubelet_size == teacher.kernel_size
         self.loss = torch.zeros(1, device=self.core.arena.device, dtype=F32)
         self.last = {}
@@ -161,7 +182,7 @@ class Stage1Engine:
             # shipped config: the loss and its gradient are fused into the decoder-tail kernels
             _, x_clip, state = core.run_forward(videos, vis_idx[0], patches_s, dp, True, True,
                                                 targets=targets, loss_acc=self.loss)
-            core.run_backward(state, targets=targets, grad_sync=self.grad_sync)
+            core.run_backward(state, targets=targets, grad_sync=None if self.nvls is not None else self.grad_sync)
         else:
             # run_stage1.py:403-408,432-433 (nn.MSELoss / nn.SmoothL1Loss / nn.L1Loss, mean reduction): loss value and
             # d loss / d outputs are a few element-wise device ops on the [K,B,Nv,C] outputs; the rest of backward is shared
@@ -180,13 +201,16 @@ class Stage1Engine:
                 g = d.sign() / n
             else:
                 raise NotImplementedError(f"clip_loss_type={kind!r} (run_stage1.py:430-435 raises for anything else too)")
-            core.run_backward(state, g_clip=g, grad_sync=self.grad_sync)
+            core.run_backward(state, g_clip=g, grad_sync=None if self.nvls is not None else self.grad_sync)
         self.last = dict(attn=attn, mask=mask.view(B, Tp * P).bool(), vis_idx=vis_idx[0], targets=targets, outputs=x_clip)
         return self.loss
 
     def _step_body_dev(self, videos, q):
         self.optimizer.zero_grad()
         self.forward_backward(videos, q, None)
+        if self.nvls is not None:
+            self.nvls.step_dev()                        # reduce-scatter + AdamW + shadow all-gather, one kernel
+            return
         if self.grad_sync is not None:
             self.grad_sync.all_reduce(self.core.arena.grads)
         self.optimizer.step_dev()
@@ -196,6 +220,10 @@ class Stage1Engine:
         if not graphable:
             self.optimizer.zero_grad()
             loss = self.forward_backward(videos, q, dp)
+            if self.nvls is not None:
+                self.optimizer.prepare_step(grad_scale=1.0 / self.nvls.world)
+                self.nvls.step_dev()
+                return loss
             scale = 1.0
             if self.grad_sync is not None:
                 scale = self.grad_sync.all_reduce(self.core.arena.grads)
