@@ -317,7 +317,7 @@ static int nvls_ctas_per_sm() { static int c = env_int("UB_NVLS_CTAS", 2); retur
 // UB_NVLS_MODE: push (default) | p2p (pull with peer loads) | mc (pull with multimem.ld_reduce)
 static int nvls_mode() { static int m = [] { const char* e = getenv("UB_NVLS_MODE"); return !e || !*e ? 2 : (e[0] == 'm' ? 0 : (e[1] == '2' ? 1 : 2)); }(); return m; }
 static bool nvls_mode_mc() { return nvls_mode() == 0; }
-static int nvls_mc_store() { static int m = env_int("UB_NVLS_MCST", -1); return m; }   // -1: multicast stores when world > 2
+static int nvls_mc_store() { static int m = env_int("UB_NVLS_MCST", 0); return m; }   // measured equal at 8 GPUs, slower at 2
 static int nvls_grid() { return sm_count() * nvls_ctas_per_sm(); }
 constexpr int kNvlsMaxCtasPerSm = 8;
 
@@ -350,7 +350,7 @@ extern "C" int ub_adamw_nvls(float* p, const float* g_mc, float* m, float* v, vo
     a.w16_peer[r] = p2p && r < world ? (uint4*)w16_peers[r] : nullptr;
     UB_REQUIRE(!p2p || r >= world || (a.g_peer[r] && a.w16_peer[r]), "adamw_nvls: null peer pointer for rank %d", r);
   }
-  a.mc_store = nvls_mc_store() < 0 ? (world > 2 ? 1 : 0) : nvls_mc_store();
+  a.mc_store = nvls_mc_store();
   int grid = nvls_grid();
   cudaStream_t st = (cudaStream_t)stream;
   int u = nvls_unroll();
