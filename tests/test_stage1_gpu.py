@@ -163,6 +163,43 @@ def test_optimizer_step_matches_torch_adamw():
     assert rel_l2(p_dev, eng.core.arena.params) < 1e-6
 
 
+def test_clip_grad_matches_torch_clip_grad_norm_then_adamw():
+    """utils.py:613-615: clip_grad_norm_(parameters, clip_grad) between backward and optimizer.step(); here the coefficient is
+    computed on the device and folded into the AdamW pass.  Checked in the clipping regime (max_norm well below the norm) and
+    in the no-op regime (max_norm above it)."""
+    from unite_b200.engine import Stage1Engine
+    fix = load_golden("tiny_stage12.pt")
+    scfg, tcfg = oracle_cfgs(fix)
+    ssd, tsd, _ = seeded_states(fix)
+    student, teacher = _models(scfg, tcfg, ssd, tsd)
+    eng = Stage1Engine(student, teacher, mask_ratio=fix["cfg"]["mask_ratio"], lr=1e-3, weight_decay=0.05)
+    videos, q = fix["videos"].cuda(), fix["q"].cuda()
+    for regime in ("clip", "noop"):
+        before = {k: v.detach().clone() for k, v in student.state_dict().items()}
+        m0, v0, t0 = eng.optimizer.exp_avg.clone(), eng.optimizer.exp_avg_sq.clone(), eng.optimizer.step_count
+        eng.optimizer.zero_grad()
+        eng.forward_backward(videos, q)
+        grads = {k: eng.core.arena.g32(k).clone() for k in before}
+        total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values())).item()
+        max_norm = total * (0.25 if regime == "clip" else 4.0)
+        eng.optimizer.step(max_norm=max_norm)
+        torch.cuda.synchronize()
+        assert abs(eng.optimizer.grad_norm().item() - total) < 1e-4 * total              # the norm BEFORE clipping is what is reported
+        ps = {k: before[k].clone().requires_grad_() for k in before}
+        dec = [p for k, p in ps.items() if not (p.ndim == 1 or k.endswith(".bias"))]
+        nod = [p for k, p in ps.items() if (p.ndim == 1 or k.endswith(".bias"))]
+        opt = torch.optim.AdamW([dict(params=dec, weight_decay=0.05), dict(params=nod, weight_decay=0.0)], lr=1e-3, betas=(0.9, 0.95), eps=1e-8)
+        # bring torch's moments to the engine's state before this step
+        for k, p in ps.items():
+            o, n = eng.core.arena.offsets[k]
+            opt.state[p] = dict(step=torch.tensor(float(t0)), exp_avg=m0[o:o + n].view_as(p).clone(), exp_avg_sq=v0[o:o + n].view_as(p).clone())
+            p.grad = grads[k].clone()
+        torch.nn.utils.clip_grad_norm_(list(ps.values()), max_norm)
+        opt.step()
+        for k, p in ps.items():
+            assert rel_l2(student.state_dict()[k], p) < 1e-6, (regime, k)
+
+
 def test_vitl_student_tubelet2_teacher_kernel2_against_oracle():
     """BASELINE configs[4] shapes: ViT-L/16 student (D=1024, 24 layers, 16 heads), 16 frames, tubelet 2, CLIP-B/16 teacher built
     with kernel_size=2 -> 1568 tokens, 320 visible.  B=1, against the oracle on the CPU."""

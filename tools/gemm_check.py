@@ -5,7 +5,7 @@ import torch
 from unite_b200 import _cabi as cabi
 
 
-def run(M, N, K, a_mn=0, b_mn=0, out_fp32=0, bias=False, act=0, resid=False, split_k=1, accumulate=0, time_it=False):
+def run(M, N, K, a_mn=0, b_mn=0, out_fp32=0, bias=False, act=0, resid=False, split_k=1, accumulate=0, time_it=False, tile_ctas=0):
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(M * 7 + N * 3 + K)
     A = torch.randn(M, K, device=dev, generator=g).bfloat16()
@@ -25,7 +25,7 @@ def run(M, N, K, a_mn=0, b_mn=0, out_fp32=0, bias=False, act=0, resid=False, spl
     if resid:
         rv = torch.randn(M, N, device=dev, generator=g)
         ep.residual = rv.data_ptr(); ep.ldr = N; ref = ref + rv; keep.append(rv)
-    ep.act = act; ep.out_fp32 = out_fp32; ep.accumulate = accumulate
+    ep.act = act; ep.out_fp32 = out_fp32; ep.accumulate = accumulate; ep.tile_ctas = tile_ctas
     Cout = torch.zeros(M, N, device=dev, dtype=torch.float32 if out_fp32 else torch.bfloat16)
     st = torch.cuda.current_stream().cuda_stream
     def call():
@@ -39,7 +39,7 @@ def run(M, N, K, a_mn=0, b_mn=0, out_fp32=0, bias=False, act=0, resid=False, spl
     rel = ((Cout.float() - ref).norm() / ref.norm()).item()
     ok = rel < (2e-3 if out_fp32 else 6e-3)
     msg = f"M={M} N={N} K={K} a_mn={a_mn} b_mn={b_mn} fp32={out_fp32} bias={bias} act={act} res={resid} split={split_k}: max_err={err:.4g} (scale {scale:.3g}) rel={rel:.3g} {'OK' if ok else 'FAIL'}"
-    if time_it and not accumulate:
+    if time_it:
         for _ in range(3): call()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n = 20

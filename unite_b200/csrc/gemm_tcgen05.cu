@@ -684,6 +684,13 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   }
   if (force_ncta == 1) ncta = 1;
   if (force_ncta == 2 && bn == 256) ncta = 2;
+  static int force_bn = -1;            // experiments: UB_GEMM_BN=128|256 overrides the tile width for every call
+  if (force_bn < 0) {
+    const char* e = getenv("UB_GEMM_BN");
+    force_bn = e ? atoi(e) : 0;
+  }
+  if (force_bn == 128) { bn = 128; ncta = 1; }
+  if (force_bn == 256 && N > 128) bn = 256;
   // per-call hint (beats the environment): used when two GEMMs are run side by side on disjoint sets of SMs
   if (ep.tile_ctas == 1) ncta = 1;
   if (ep.tile_ctas == 2 && bn == 256 && M > BM) ncta = 2;

@@ -57,13 +57,29 @@ class FusedAdamW:
                                math.sqrt(1.0 - b2 ** self.step_count), grad_scale], dtype=F32))
         self._hyper_dev.copy_(hp, non_blocking=True)
 
-    def step_dev(self):
-        """Device side: grad-norm + AdamW reading the scalars uploaded by prepare_step (capturable in a CUDA graph)."""
+    def step_dev(self, max_norm: Optional[float] = None):
+        """Device side: grad-norm + AdamW reading the scalars uploaded by prepare_step (capturable in a CUDA graph).
+        max_norm: utils.py:613-615 (torch.nn.utils.clip_grad_norm_ before the step): the norm must be known before the
+        update, so it takes its own sweep (ub_sumsq); the clip coefficient min(1, max_norm / (norm + 1e-6)) is folded into
+        the kernel's grad_scale on the device — no host read, the gradients themselves are not rewritten."""
         a = self.arena
         self.gnorm_sq.zero_()
-        ops.adamw_dev(a.params, a.grads, self.exp_avg, self.exp_avg_sq, a.w16, a.n_decay, self._hyper_dev, self.gnorm_sq)
+        if not max_norm:
+            ops.adamw_dev(a.params, a.grads, self.exp_avg, self.exp_avg_sq, a.w16, a.n_decay, self._hyper_dev, self.gnorm_sq)
+            return
+        ops.sumsq(a.grads, self.gnorm_sq)
+        if not hasattr(self, "_hyper_clip"):
+            self._hyper_clip = torch.zeros_like(self._hyper_dev)
+        h = self._hyper_clip
+        h.copy_(self._hyper_dev)
+        norm = self.gnorm_sq.sqrt() * self._hyper_dev[7:8]               # norm of the AVERAGED gradients (the arena holds rank sums)
+        h[7:8] = self._hyper_dev[7:8] * (max_norm / (norm + 1e-6)).clamp(max=1.0)
+        ops.adamw_dev(a.params, a.grads, self.exp_avg, self.exp_avg_sq, a.w16, a.n_decay, h, None)
 
-    def step(self, grad_scale: float = 1.0):
+    def step(self, grad_scale: float = 1.0, max_norm: Optional[float] = None):
+        if max_norm:
+            self.prepare_step(grad_scale=grad_scale)
+            return self.step_dev(max_norm=max_norm)
         a = self.arena
         self.step_count += 1
         self.gnorm_sq.zero_()
@@ -102,6 +118,7 @@ class Stage1Engine:
         self.student, self.teacher, self.mask_ratio = student, teacher, mask_ratio
         self.use_graph = use_graph
         self.clip_loss_type = clip_loss_type
+        self.max_norm = None                  # clip_grad of the reference's loss_scaler call (run_stage1.py:451-455); None / 0 = off
         self._graphs = {}
         self._graph_count, self._graph_pool = {}, None
         self.max_graphs_per_shape = int(os.environ.get("UB_MAX_GRAPHS", "6"))   # 0: always copy into private static inputs
@@ -211,11 +228,17 @@ class Stage1Engine:
         self.optimizer.zero_grad()
         self.forward_backward(videos, q, None)
         if self.nvls is not None:
+            self._no_clip_with_nvls()
             self.nvls.step_dev()                        # reduce-scatter + AdamW + shadow all-gather, one kernel
             return
         if self.grad_sync is not None:
             self.grad_sync.all_reduce(self.core.arena.grads)
-        self.optimizer.step_dev()
+        self.optimizer.step_dev(max_norm=self.max_norm)
+
+    def _no_clip_with_nvls(self):
+        if self.max_norm:
+            raise NotImplementedError("clip_grad needs the norm of the SUMMED gradient before the update; the fused NVLink step "
+                                      "reduces and updates in one pass — run with UB_DDP_NVLS=0 when clipping")
 
     def step(self, videos, q, dp=None):
         graphable = self.use_graph and dp is None and not (self.student.training and any(r > 0 for r in self.student.encoder.drop_path_rates))
@@ -223,15 +246,16 @@ class Stage1Engine:
             self.optimizer.zero_grad()
             loss = self.forward_backward(videos, q, dp)
             if self.nvls is not None:
+                self._no_clip_with_nvls()
                 self.optimizer.prepare_step(grad_scale=1.0 / self.nvls.world)
                 self.nvls.step_dev()
                 return loss
             scale = 1.0
             if self.grad_sync is not None:
                 scale = self.grad_sync.all_reduce(self.core.arena.grads)
-            self.optimizer.step(grad_scale=scale)
+            self.optimizer.step(grad_scale=scale, max_norm=self.max_norm)
             return loss
-        shape_key = (tuple(videos.shape), videos.dtype, tuple(q.shape), self.clip_loss_type)
+        shape_key = (tuple(videos.shape), videos.dtype, tuple(q.shape), self.clip_loss_type, float(self.max_norm or 0.0))
         scale = 1.0 / self.grad_sync.world if self.grad_sync is not None else 1.0
         self.optimizer.prepare_step(grad_scale=scale)
         n = self._eager_steps.get(shape_key, 0)

@@ -44,11 +44,10 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
                                   "(configs/stage1_config.yaml)")
     if clip_loss_type not in ("l2", "mse", "smooth_l1", "l1"):
         raise NotImplementedError(f"clip_loss_type={clip_loss_type!r}")                  # run_stage1.py:434-435
-    if max_norm:
-        raise NotImplementedError("clip_grad is null in every shipped config")
     model.train()
     eng = _engine_for(model, teacher_model, mask_ratio, optimizer, use_graph=bool(getattr(args, "use_cuda_graph", False)))
     eng.clip_loss_type = clip_loss_type
+    eng.max_norm = float(max_norm) if max_norm else None       # loss_scaler(..., clip_grad=max_norm, ...), run_stage1.py:451-455
     opt = eng.optimizer
     dev = eng.core.arena.device
     log_freq = getattr(args, "log_freq", 10) if args is not None else 10
