@@ -19,6 +19,6 @@ def test_fused_step_matches_nccl_then_adamw(mode):
     world = 8 if n_gpu >= 8 else (4 if n_gpu >= 4 else 2)
     env = dict(os.environ, UB_NVLS_MODE=mode)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-                        "--master-port", "29561", os.path.join(ROOT, "tools", "nvls_check.py"), "--n", "8808040", "--iters", "3"],
+                        "--master-port", "29561", os.path.join(ROOT, "tools", "nvls_check.py"), "--numel", "8808040", "--iters", "3"],
                        capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert r.returncode == 0 and "PARITY OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])

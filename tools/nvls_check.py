@@ -1,6 +1,6 @@
 """Parity + timing of the fused NVLS optimizer step (csrc/ddp_nvls.cu) against NCCL all-reduce -> ub_adamw_dev.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tools/nvls_check.py [--n 88080384]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tools/nvls_check.py [--numel 88080384]
 
 Every rank draws its own gradients; both paths start from identical p / m / v and run 3 steps.  After consolidate() the
 sharded fp32 state must equal the replicated reference to 1e-5 relative (the two kernels contract FMAs differently; at
@@ -21,7 +21,7 @@ import torch.distributed as dist
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=88_080_384)
+    ap.add_argument("--numel", dest="n", type=int, default=88_080_384)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--iters", type=int, default=10)
     args = ap.parse_args()
