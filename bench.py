@@ -125,6 +125,10 @@ def cpu_reference_run(steps, warmup, batch=2, seed=0):
                 ms_per_step=dt * 1e3, loss=float(r["loss"]))
 
 
+WORKLOAD = ("BASELINE configs[1]: stage-1 UMT masked distillation, ViT-B/16 student (80% CLIP-attn mask, 320 of 1568 tokens) + "
+            "frozen CLIP ViT-B/16 teacher, 8x224^2, tubelet 1, K=6 aligned layers, AdamW")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -133,8 +137,9 @@ def run_reference(args):
     cb = cpu_reference_run(steps, warm)
     line = dict(metric=METRIC, value=cb["value"], unit="clips/s", n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=cb["ms_per_step"],
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="stage-1 UMT distillation step, ViT-B/16 student + CLIP ViT-B/16 teacher, 8x224^2, mask 0.8, tubelet 1; "
-                                     "CPU sample B=2 clips/step", global_batch=2, l2_policy="n/a (CPU)"),
+                config=dict(workload=WORKLOAD, per_gpu_batch=args.batch, global_batch=args.batch * args.gpus, parallelism=f"dp{args.gpus}",
+                            cpu_sample="each step = B=2 clips of that workload (teacher fwd + mask + student fwd/bwd), fp32 torch CPU, all host "
+                                       "threads; clips/s does not depend on the batch the sample is cut from", l2_policy="n/a (CPU)"),
                 cpu_baseline=dict(kind=cb["kind"], cores=cb["cores"], sample=cb["sample"], value=cb["value"], unit="clips/s"),
                 e2e=dict(value=cb["value"], unit="clips/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -353,9 +358,7 @@ def main():
     line = dict(
         metric=METRIC, value=round(value, 2), unit="clips/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=round(ms_per_step, 3), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-        config=dict(workload="BASELINE configs[1]: stage-1 UMT masked distillation, ViT-B/16 student (80% CLIP-attn mask, 320 of 1568 tokens) + "
-                             "frozen CLIP ViT-B/16 teacher, 8x224^2, tubelet 1, K=6 aligned layers, AdamW",
-                    per_gpu_batch=B, global_batch=B * world, parallelism=f"dp{world}", cuda_graph=use_graph, l2_policy="inputs_exceed_l2 (154 MB clip batch + "
+        config=dict(workload=WORKLOAD, per_gpu_batch=B, global_batch=B * world, parallelism=f"dp{world}", cuda_graph=use_graph, l2_policy="inputs_exceed_l2 (154 MB clip batch + "
                     "multi-GB activations per step vs 126 MB L2; two input batches alternate)", init="random (reference initialisers), seed 0"),
         clocks=clocks,
         e2e=dict(value=round(e2e_value, 2), unit="clips/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=round(e2e_ms, 3),
