@@ -206,7 +206,10 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(args.warmup):
+    # untimed warm-up: W steps, and at least 2 eager steps + one CUDA-graph capture per resident input buffer (the engine keeps
+    # one graph per buffer pair), so that no capture can fall inside the timed region whatever W the caller asked for
+    n_warm = max(args.warmup, 2 + len(dev_batches))
+    for i in range(n_warm):
         eng.step(*dev_batches[i % 2])
     sync_all()
     sampler = ClockSampler(local)
