@@ -66,6 +66,8 @@ typedef struct ub_gemm_epilogue {
   float* stats_out;     /* residual_f16 epilogue only: += row (sum, sumsq) of the fp16 values written to C (must be zeroed)  */
   float ln_inv_d;
   float ln_eps;
+  float* colsum_out;    /* DGELU epilogue only: += column sums over the M rows of the values written to C — the bias gradient of
+                         * the Linear whose pre-activation is aux_in (saves the separate pass over C)                          */
 } ub_gemm_epilogue;
 
 /* a_mn_major / b_mn_major = 1: the operand is stored transposed, i.e. A is [K, lda>=M] / B is [K, ldb>=N]

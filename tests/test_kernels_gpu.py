@@ -59,6 +59,33 @@ def test_gemm_all_operand_majors_and_epilogues():
     assert ok
 
 
+@pytest.mark.parametrize("M,N,K", [(2048, 3072, 768), (1000, 520, 256), (10240, 3072, 768)])
+def test_gemm_dgelu_epilogue_with_fused_bias_gradient(M, N, K):
+    """dX = (dY @ W) * gelu'(pre) in bf16 and, from the same epilogue, colsum_out += sum over rows of dX (the fc1 bias gradient,
+    modeling_finetune.py:66-73 backward).  Reference: fp32 torch on the same bf16 operands; ragged M / N / K included."""
+    import torch
+    from unite_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    dy = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(K, N, device="cuda", generator=g) * 0.05).bfloat16()            # stored [K, N]: b_t form, as in backward
+    pre = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    bias_grad = torch.full((N,), 3.0, device="cuda")                                 # accumulates on top of what is there
+    ops.gemm(dy, w, out, b_t=True, act=ops.UB_ACT_DGELU, aux_in=pre, colsum_out=bias_grad)
+    torch.cuda.synchronize()
+    x = pre.float()
+    dgelu = 0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * torch.pi) ** 0.5
+    ref = (dy.float() @ w.float()) * dgelu
+    assert ((out.float() - ref).norm() / ref.norm()).item() < 6e-3
+    ref_sum = ref.sum(0) + 3.0
+    err = (bias_grad - ref_sum).abs().max().item()
+    assert err < 2e-3 * ref.abs().sum(0).max().item() + 1e-3, err
+    # and against the separate pass over the bf16 output it replaces
+    sep = torch.full((N,), 3.0, device="cuda")
+    ops.colsum_bf16(out, sep)
+    assert (bias_grad - sep).abs().max().item() < 5e-3 * out.float().abs().sum(0).max().item() + 1e-3
+
+
 def test_gemm_layernorm_fold_and_fp16_residual_statistics():
     """Teacher path: x = residual + A W^T written in fp16 with its row (sum, sumsq); the next GEMM consumes x directly and applies
     LayerNorm in its epilogue (fp16 operands).  Against torch layer_norm + linear in fp32."""

@@ -35,6 +35,7 @@ class GemmEpilogue(C.Structure):
         ("stats_out", C.c_void_p),
         ("ln_inv_d", C.c_float),
         ("ln_eps", C.c_float),
+        ("colsum_out", C.c_void_p),
     ]
 
 

@@ -46,6 +46,7 @@ struct GemmParams {
   const float* ln_c;        //                 column sums of B
   float ln_inv_d, ln_eps;
   float* stats_out;         // EPI 3: row (sum, sumsq) of the fp16 output
+  float* colsum_out;        // EPI 2: += column sums of the values written to C (the bias gradient of the Linear that produced aux)
 };
 
 // EPI : 0 = bias / activation (/ pre-activation copy), 1 = + fp32 residual (fp32 out), 2 = DGELU: * gelu'(aux) (bf16 out),
@@ -387,6 +388,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= rscale;
           }
+          if (EPI == 2 && p.colsum_out != nullptr) {
+            // column sums over this warp's 32 rows (rows past M are exact zeros: A and the pre-activation are zero-filled by
+            // TMA): recursive halving — at each step a lane keeps one half of its columns and hands the other half to its
+            // partner — 31 shuffles, after which lane L holds the total of column L of this 32-column group
+            float s[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s[i] = v[i];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool upper = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float give = upper ? s[i] : s[i + off];
+                const float keep = upper ? s[i + off] : s[i];
+                s[i] = keep + __shfl_xor_sync(0xffffffffu, give, off);
+              }
+            }
+            const int gcol = col0 + h * 32 + lane;
+            if (gcol < p.N) atomicAdd(p.colsum_out + gcol, s[0]);
+          }
           if (OUT32) {
             // fp32 slab: 8 chunks of 4 floats; EPI 1 adds the residual that TMA placed in the same slab
 #pragma unroll
@@ -641,6 +662,7 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
              "gemm: the LayerNorm fold works with the bias / activation epilogue only");
   UB_REQUIRE(ep.stats_out == nullptr || ep.residual_f16, "gemm: stats_out belongs to the fp16-residual epilogue");
   UB_REQUIRE(ep.act != UB_ACT_DGELU || !ep.out_fp32, "gemm: the DGELU epilogue writes bf16");
+  UB_REQUIRE(ep.colsum_out == nullptr || ep.act == UB_ACT_DGELU, "gemm: colsum_out belongs to the DGELU epilogue");
   UB_REQUIRE(ep.residual == nullptr || (ep.act == UB_ACT_NONE && !ep.accumulate),
              "gemm: residual cannot be combined with an activation / accumulate");
   UB_REQUIRE(ep.aux_out == nullptr || (ep.act == UB_ACT_GELU && !ep.out_fp32), "gemm: aux_out is the bf16 GELU pre-activation copy");
@@ -726,6 +748,7 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   p.ab_f16 = ep.ab_f16;
   p.ln_stats = ep.ln_stats; p.ln_c = ep.ln_c; p.ln_inv_d = ep.ln_inv_d; p.ln_eps = ep.ln_eps;
   p.stats_out = ep.stats_out;
+  p.colsum_out = ep.colsum_out;
   const long total_work = (long)((M + BM * ncta - 1) / (BM * ncta)) * ((N + bn - 1) / bn) * split_k;
   int units = ncta == 4 ? units4 : sms / ncta;
   if (ep.max_ctas > 0 && ep.max_ctas / ncta >= 1 && ep.max_ctas / ncta < units) units = ep.max_ctas / ncta;

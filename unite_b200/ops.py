@@ -70,10 +70,11 @@ def _p2d(t: torch.Tensor, dtype, what):
 @_instrument("gemm", 1)
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=False, bias=None, residual=None,
          row_scale=None, rows_per_scale=0, act=UB_ACT_NONE, aux_in=None, aux_out=None, accumulate=False, split_k=1, tile_ctas=0,
-         max_ctas=0, ln_stats=None, ln_c=None, ln_eps=0.0, stats_out=None):
+         max_ctas=0, ln_stats=None, ln_c=None, ln_eps=0.0, stats_out=None, colsum_out=None):
     """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).  a_t / b_t: the operand is stored transposed ([K,M] / [K,N]).
     A and B are both bf16 or both fp16.  ln_stats / ln_c: LayerNorm of A's rows folded into the epilogue (see the header);
-    stats_out: row (sum, sumsq) of an fp16-residual output, accumulated."""
+    stats_out: row (sum, sumsq) of an fp16-residual output, accumulated.  colsum_out (DGELU epilogue): fp32 [N], += column sums
+    of the output over its M rows (the bias gradient of the Linear whose pre-activation is aux_in)."""
     ab = F16 if a.dtype == F16 else BF16
     pa, lda = _p2d(a, ab, "gemm A")
     pb, ldb = _p2d(b, ab, "gemm B")
@@ -125,6 +126,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=
         if tuple(stats_out.shape) != (M, 2):
             raise _cabi.UBError("gemm: stats_out must be fp32 [M,2]")
         ep.stats_out = _p(stats_out, F32, "stats_out")
+    if colsum_out is not None:
+        if colsum_out.numel() != N:
+            raise _cabi.UBError("gemm: colsum_out must be fp32 [N]")
+        ep.colsum_out = _p(colsum_out, F32, "colsum_out")
     check(lib.ub_gemm_bf16(pa, lda, int(a_t), pb, ldb, int(b_t), pc, ldc, M, N, K, C.byref(ep), split_k, _stream()), "ub_gemm_bf16")
     return out
 
