@@ -286,9 +286,9 @@ class Stage1Engine:
                     self._graph_pool = g.pool()
                 n_kernels = ops.LAUNCHES - n0           # kernels of ours recorded in the graph (capture executes nothing)
                 ops.LAUNCHES = n0
-                self._graphs[buf_key] = (g, sv, sq, n_kernels)
+                self._graphs[buf_key] = (g, sv, sq, n_kernels, self.last)     # `last` = this graph's own mask / target / output tensors
                 self._graph_count[shape_key] = self._graph_count.get(shape_key, 0) + 1
-        g, sv, sq, n_kernels = self._graphs[buf_key]
+        g, sv, sq, n_kernels, self.last = self._graphs[buf_key]
         ops.LAUNCHES += n_kernels                       # every replay launches all of them
         if videos.data_ptr() != sv.data_ptr():
             sv.copy_(videos, non_blocking=True)
