@@ -54,7 +54,8 @@ typedef struct ub_gemm_epilogue {
   int32_t out_fp32; /* 0: C is bf16, 1: C is fp32                                                         */
   int32_t accumulate; /* 1: C (fp32) += result with red.add (required when split_k > 1)                   */
   int32_t tile_ctas;  /* scheduling hint: 0 = cost model, 1 / 2 / 4 = CTAs per work item (4 = two pairs + B multicast) */
-  int32_t max_ctas;   /* scheduling hint: 0 = whole device, else cap on the persistent grid (a GEMM run beside another)  */
+  int32_t max_ctas;   /* scheduling hint: 0 = whole device, > 0 = cap on the persistent grid (a GEMM run beside another),
+                       * < 0 = non-persistent: one CTA (pair) per work item, for off-critical-path GEMMs on a low-priority stream */
   int32_t residual_f16; /* 1: `residual` is fp16 [M, ldr] and C is fp16 too (out_fp32 must be 0): the teacher's residual stream */
   int32_t ab_f16;       /* 1: A and B hold fp16 (not bf16) values                                                          */
   /* LayerNorm folded into the GEMM (frozen teacher): with A = the raw residual stream x (fp16), B = gamma o W, ln_c[n] =

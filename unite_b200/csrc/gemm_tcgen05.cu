@@ -752,6 +752,10 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   const long total_work = (long)((M + BM * ncta - 1) / (BM * ncta)) * ((N + bn - 1) / bn) * split_k;
   int units = ncta == 4 ? units4 : sms / ncta;
   if (ep.max_ctas > 0 && ep.max_ctas / ncta >= 1 && ep.max_ctas / ncta < units) units = ep.max_ctas / ncta;
+  // max_ctas < 0: one CTA (pair) per work item — a NON-persistent grid.  Meant for GEMMs that are off the critical path (weight
+  // gradients) and run on a low-priority stream: their short-lived CTAs fill SMs the critical path leaves idle, and the block
+  // scheduler can hand an SM back to the high-priority stream at every CTA boundary instead of after a whole static tile list.
+  if (ep.max_ctas < 0) units = (int)(total_work < 65535 ? total_work : 65535);
   const int grid = (int)(total_work < units ? total_work : units) * ncta;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 

@@ -280,7 +280,14 @@ class Stage1Engine:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 n0 = ops.LAUNCHES
-                with torch.cuda.graph(g, pool=self._graph_pool):
+                # UB_SIDE_WGRAD=2: capture on a high-priority stream so that the kernel nodes of the critical path outrank the
+                # low-priority side stream of the weight-gradient GEMMs (vit_core._SIDE_WGRAD_FINE)
+                cap_stream = None
+                if os.environ.get("UB_SIDE_WGRAD", "0") == "2":
+                    if getattr(self, "_hi_stream", None) is None:
+                        self._hi_stream = torch.cuda.Stream(device=self.core.arena.device, priority=-1)
+                    cap_stream = self._hi_stream
+                with torch.cuda.graph(g, pool=self._graph_pool, stream=cap_stream):
                     self._step_body_dev(sv, sq)
                 if self._graph_pool is None:
                     self._graph_pool = g.pool()

@@ -27,7 +27,13 @@ BF16, F32 = torch.bfloat16, torch.float32
 
 # measured on B200 (round 1): no gain — every GEMM is a persistent one-CTA-per-SM grid, so two of them cannot share SMs and
 # the tails they could fill are short; kept as an option (UB_SIDE_WGRAD=1)
-_SIDE_WGRAD = os.environ.get("UB_SIDE_WGRAD", "0") == "1"
+_SIDE_WGRAD = os.environ.get("UB_SIDE_WGRAD", "0") in ("1", "2")
+# UB_SIDE_WGRAD=2 (written at the end of round 1, NOT yet measured on a GPU): the side-stream weight-gradient GEMMs become
+# NON-persistent single-CTA grids with finer split-K (work items of ~24 k-blocks) while the step itself is captured on a
+# high-priority stream (engine.Stage1Engine), so the block scheduler fills idle SMs with weight-gradient CTAs and hands every SM
+# back to the critical path at the next CTA boundary.  The persistent form could not do that: its CTAs keep an SM for their
+# whole static tile list, which is why UB_SIDE_WGRAD=1 measured no gain.
+_SIDE_WGRAD_FINE = os.environ.get("UB_SIDE_WGRAD", "0") == "2"
 # fc1 bias gradient accumulated by the epilogue of the GEMM that produces d_pre (ub_gemm_epilogue.colsum_out) instead of a
 # separate column-sum pass over d_pre: 12 launches and 12 x 63 MB of reads fewer per ViT-B step
 _FUSE_COLSUM = os.environ.get("UB_FUSE_COLSUM", "0") == "1"
@@ -95,7 +101,7 @@ class ViTTrunk:
 
     def _side_stream(self):
         if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=self.arena.device)
+            self._side = torch.cuda.Stream(device=self.arena.device, priority=0)     # lowest priority
         return self._side
 
     # -- parameter access ---------------------------------------------------------------------
@@ -166,6 +172,10 @@ class ViTTrunk:
     # -- backward -----------------------------------------------------------------------------
     def _wgrad(self, dy, x_in, gw):
         """gw[out,in] += dy[M,out]^T @ x_in[M,in]  (contraction over tokens, both operands MN-major)."""
+        if _SIDE_WGRAD_FINE and dy.is_cuda:
+            kb = (dy.shape[0] + 63) // 64                                  # k-blocks of the token contraction
+            ops.gemm(dy, x_in, gw, a_t=True, b_t=True, accumulate=True, split_k=max(1, min(32, kb // 24)), tile_ctas=1, max_ctas=-1)
+            return
         ops.gemm(dy, x_in, gw, a_t=True, b_t=True, accumulate=True, split_k=_splits_for(gw.shape[0], gw.shape[1], self.sms))
 
     def backward(self, ws: TrunkWorkspace, tap_grads: Dict[int, callable], dx_init: bool = False, on_block_done=None):
