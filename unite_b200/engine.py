@@ -144,6 +144,21 @@ class Stage1Engine:
         self.loss = torch.zeros(1, device=self.core.arena.device, dtype=F32)
         self.last = {}
 
+    def set_optimizer(self, optimizer: "FusedAdamW"):
+        """Swap in a caller-built FusedAdamW over the same arena (train_one_epoch's `optimizer` argument); the fused data-parallel
+        step, if active, is re-bound to it (its gradient-norm accumulator lives in symmetric memory)."""
+        if optimizer is self.optimizer:
+            return
+        if optimizer.arena is not self.core.arena:
+            raise ValueError("the optimizer was built over a different parameter arena than this engine's student")
+        if self.nvls is not None:
+            self.nvls.opt = optimizer
+            optimizer.gnorm_sq = self.optimizer.gnorm_sq
+            optimizer._sharded = self.nvls
+        self.optimizer = optimizer
+        self._graphs.clear()                    # captured graphs hold the old optimizer's buffers
+        self._graph_count.clear()
+
     def n_visible(self, P):
         return P - int(P * self.mask_ratio)                      # run_stage1.py:380
 

@@ -28,7 +28,7 @@ def _engine_for(model, teacher_model, mask_ratio, optimizer, use_graph=False):
             gs.arena = student.core().arena
         _ENGINES[key] = Stage1Engine(student, teacher, mask_ratio=mask_ratio, grad_sync=gs, use_graph=use_graph)
         if optimizer is not None and hasattr(optimizer, "arena"):
-            _ENGINES[key].optimizer = optimizer
+            _ENGINES[key].set_optimizer(optimizer)
     return _ENGINES[key]
 
 
