@@ -361,7 +361,9 @@ def main():
     line = dict(
         metric=METRIC, value=round(value, 2), unit="clips/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=round(ms_per_step, 3), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16", data="synthetic",
-        config=dict(workload=WORKLOAD, per_gpu_batch=B, global_batch=B * world, parallelism=f"dp{world}", cuda_graph=use_graph, l2_policy="inputs_exceed_l2 (154 MB clip batch + "
+        config=dict(workload=WORKLOAD, per_gpu_batch=B, global_batch=B * world, parallelism=f"dp{world}", cuda_graph=use_graph,
+                    warmup_steps_run=n_warm, ddp=("fused NVLink step (ub_adamw_nvls)" if getattr(eng, "nvls", None) is not None else ("NCCL all-reduce" if world > 1 else "n/a")),
+                    l2_policy="inputs_exceed_l2 (154 MB clip batch + "
                     "multi-GB activations per step vs 126 MB L2; two input batches alternate)", init="random (reference initialisers), seed 0"),
         clocks=clocks,
         e2e=dict(value=round(e2e_value, 2), unit="clips/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=round(e2e_ms, 3),
