@@ -119,10 +119,14 @@ UB_API int ub_layernorm_bwd(const void* dy, const float* x, const float* gamma, 
                             float* dx_out, void* dxs_out, const float* row_scale, int rows_per_scale, float* dgamma,
                             float* dbeta, float* dsum /* optional: += column sums of dxs (fp32) */, int rows, int D,
                             void* stream);
+/* [loss_row_lo, loss_row_hi) / [go_row_lo, go_row_hi): the rows that take part in the loss and receive the upstream gradient — all
+ * rows for clip_loss_data 'mixed', the first B_s clips for 'source', the rest for 'target' (run_stage1.py:418-423); rows outside
+ * the range are still normalised and written by fwd, and get a zero gradient from bwd. */
 UB_API int ub_dec_tail_fwd(const float* y, const float* gamma, const float* beta, float eps, float* out, const float* tgt,
-                           float* loss_acc, float loss_scale, int rows, int D, void* stream);
+                           float* loss_acc, float loss_scale, int loss_row_lo, int loss_row_hi, int rows, int D, void* stream);
 UB_API int ub_dec_tail_bwd(const float* y, const float* gamma, const float* beta, float eps, const float* go,
-                           float go_scale, void* dy_out, float* dgamma, float* dbeta, int rows, int D, void* stream);
+                           float go_scale, int go_row_lo, int go_row_hi, void* dy_out, float* dgamma, float* dbeta, int rows, int D,
+                           void* stream);
 UB_API int ub_l2norm_rows(float* x, int rows, int D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -163,7 +167,24 @@ UB_API int ub_adamw(float* p, const float* g, float* m, float* v, void* w_bf16 /
  * by this very pass — the global gradient norm of utils.py:631-643 without a second sweep over the arena. */
 UB_API int ub_adamw_dev(float* p, const float* g, float* m, float* v, void* w_bf16 /* may be NULL */, int64_t n,
                         int64_t n_decay, const float* hyper, float* gnorm_sq /* may be NULL */, void* stream);
+/* Segmented form — the parameter groups of src/optim_factory.py:76-118 with a LayerDecayValueAssigner (run_stage2.py:616-617,
+ * configs/stage2_config.yaml layer_decay 0.65): the arena is n_seg (<= 128) contiguous groups, seg_end4[s] (device int32) = end of
+ * group s in units of 4 elements (ascending, last == n/4); hyper (device) = [-, -, beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t),
+ * grad_scale, lr[n_seg], wd[n_seg]] with lr[s] = schedule value * lr_scale of the group (engine_for_finetuning.py:76-81).
+ * wd[s] < 0 marks a frozen group (requires_grad=False: left out of every group at optim_factory.py:83-84): untouched, and not
+ * part of the gradient norm.  ub_sumsq_seg is the matching norm for clip_grad (frozen groups skipped). */
+UB_API int ub_adamw_seg(float* p, const float* g, float* m, float* v, void* w_bf16 /* may be NULL */, int64_t n,
+                        const int32_t* seg_end4, int n_seg, const float* hyper, float* gnorm_sq /* may be NULL */, void* stream);
+UB_API int ub_sumsq_seg(const float* g, int64_t n, const int32_t* seg_end4, int n_seg, const float* hyper, float* out,
+                        void* stream);
 UB_API int ub_cast_bf16(const float* x, void* out, int64_t n, void* stream);
+
+/* DropPath factors for one step (src/models/modeling_finetune.py:42-50 via timm drop_path; rates = linspace(0, drop_path, depth),
+ * :311): out fp32 [depth, 2, B] = floor(keep_l + u) / keep_l, u ~ U[0,1) from Philox4x32-10 keyed by `seed` with counter
+ * (element / 4, 0, *step); the kernel then advances the DEVICE counter *step by one, so a captured launch draws fresh factors on
+ * every CUDA-graph replay.  rates: device fp32 [depth].  Consumed as ub_gemm_epilogue.row_scale (forward) and as the row_scale of
+ * ub_layernorm_bwd / ub_cast_scale_bf16 (backward). */
+UB_API int ub_drop_path_draw(const float* rates, float* out, int depth, int B, uint64_t seed, uint64_t* step, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Data-parallel optimizer step fused with its collective (replaces DistributedDataParallel's bucketed all-reduce,
@@ -173,8 +194,10 @@ UB_API int ub_cast_bf16(const float* x, void* out, int64_t n, void* stream);
  * `gnorm_sq_mc`, `flags_mc` are MULTICAST addresses of symmetric allocations (same size and offset on every rank);
  * `w16`, `flags` the rank's own mappings of the same memory.  p / m / v are local; their decay segment is updated on the
  * owning rank only (ZeRO-1), the no-decay segment on every rank.  flags: ub_nvls_slots() zero-initialised uint32 (symmetric),
- * epoch: ub_nvls_slots()/2 zero-initialised uint32 (local), err: one int32 (local; 1 / 2 = a peer never reached the entry /
- * exit barrier within ~30 s — the kernel then finishes instead of hanging).  hyper[8] as for ub_adamw_dev with
+ * epoch: ub_nvls_slots()/2 zero-initialised uint32 (local), err: one zero-initialised int32 (local; 1 / 2 / 3 = a peer never
+ * reached the entry / exit / mid barrier within UB_NVLS_SPIN_S seconds (default 120).  The error is STICKY: the CTA that gave up
+ * applies no update, and every later launch returns immediately without touching p / m / v or the shadows, so a stalled rank
+ * can never train on partial gradient sums; the host polls err at its log points and raises on every rank).  hyper[8] as for ub_adamw_dev with
  * grad_scale = 1/world.  Every rank must launch it the same number of times.
  * g_peers / w16_peers (host arrays of `world` device pointers, by rank: every rank's mapping of the gradient arena / shadow,
  * own rank included): when given and world is 2, 4 or 8 the gradients are read with plain NVLink peer loads and summed in

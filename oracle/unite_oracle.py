@@ -303,10 +303,12 @@ def alignment_loss(outputs: Tensor, targets: Tensor, kind: str = "l2") -> Tensor
 # --------------------------------------------------------------------------------------------------
 def stage1_step(student_sd: SD, teacher_sd: SD, videos: Tensor, q: Tensor, scfg: StudentCfg, tcfg: TeacherCfg,
                 mask_ratio: float = 0.8, keep_scales: Optional[Tensor] = None, with_grads: bool = True,
-                attn_override: Optional[Tensor] = None, clip_loss_type: str = "l2"):
-    """One UMT masked-distillation step with mask_type='attention', clip_loss_type='l2',
-    clip_loss_data='mixed', src_classifier=None.  q = Exp(1) noise [B*T', HW] consumed by the mask sampler.
-    Returns a dict with every intermediate the parity tests compare."""
+                attn_override: Optional[Tensor] = None, clip_loss_type: str = "l2", clip_loss_data: str = "mixed",
+                n_source: Optional[int] = None):
+    """One UMT masked-distillation step with mask_type='attention', src_classifier=None.  q = Exp(1) noise [B*T', HW] consumed
+    by the mask sampler.  clip_loss_data 'source' / 'target' (run_stage1.py:418-423): only the first n_source (= B_s) clips /
+    the remaining ones enter the loss; 'mixed' (:424-425) uses all.  Returns a dict with every intermediate the parity tests
+    compare (outputs / targets are the UNSLICED tensors)."""
     B = videos.shape[0]
     with torch.no_grad():
         feat, attn = teacher_forward(teacher_sd, videos, tcfg)                        # :375
@@ -316,7 +318,14 @@ def stage1_step(student_sd: SD, teacher_sd: SD, videos: Tensor, q: Tensor, scfg:
         targets = feat[~mask.unsqueeze(0).repeat(K, 1, 1)].reshape(K, B, -1, C)        # :389-393
     params = {k: v.detach().clone().requires_grad_(with_grads) for k, v in student_sd.items()}
     out = student_forward(params, videos, mask, scfg, clip_only=True, keep_scales=keep_scales)   # :415
-    loss = alignment_loss(out, targets, clip_loss_type)                               # :430-433
+    if clip_loss_data == "source":
+        loss = alignment_loss(out[:, :n_source], targets[:, :n_source], clip_loss_type)                 # :418-420
+    elif clip_loss_data == "target":
+        loss = alignment_loss(out[:, n_source:], targets[:, n_source:], clip_loss_type)                 # :421-423
+    elif clip_loss_data == "mixed":
+        loss = alignment_loss(out, targets, clip_loss_type)                           # :430-433
+    else:
+        raise NotImplementedError(clip_loss_data)                                      # :426-427
     res = dict(attn=attn, mask=mask, vis_idx=visible_indices(mask), targets=targets, outputs=out.detach(),
                loss=loss.detach())
     if with_grads:
@@ -397,27 +406,36 @@ def pseudo_label_fusion(logits_full_t: Tensor, logits_masked_t: Tensor, clip_pro
 
 def stage3_step(student_sd: SD, teacher_sd: SD, cls_w: Tensor, cls_b: Tensor, text_features: Tensor, videos_s: Tensor,
                 labels_s: Tensor, videos_t: Tensor, scfg: StudentCfg, tcfg: TeacherCfg, mask_ratio: float = 0.8, k: int = 2,
-                clip_threshold: float = 0.5, src_ratio: float = 1.0, tgt_ratio: float = 1.0, with_grads: bool = True):
+                clip_threshold: float = 0.5, src_ratio: float = 1.0, tgt_ratio: float = 1.0, with_grads: bool = True,
+                videos_t_aug: Optional[Tensor] = None, keep_scales: Optional[dict] = None):
     """Collaborative self-training step, masking_type='clip_attention', selection_strategy='clip_matchORconf',
     train_masked=True, conf_weighted_loss=True (run_stage3.py:427-642).  The OpenAI-CLIP zero-shot tower (absent here) is
-    replaced by the teacher trunk's CLS embedding and the given text matrix; src_classifier is frozen (run_stage3.py:1193,1264)."""
+    replaced by the teacher trunk's CLS embedding and the given text matrix; src_classifier is frozen (run_stage3.py:1193,1264).
+    videos_t_aug: the augmented view of the target clips (return_aug_for_val, run_stage3.py:405-413): it replaces videos_t for the
+    teacher attention (:434-451, `videos[B_s:]`) and the masked committee (:499); the full-token target pass (:480) and the
+    zero-shot head (:557) keep the plain view.  keep_scales: optional DropPath factors per forward, keys 's', 't', 'm'
+    ([depth,2,B] each; 'm' has k*B_t samples) — the model is in train mode for every pass (:352)."""
     Bs, Bt = videos_s.shape[0], videos_t.shape[0]
+    v_mask = videos_t if videos_t_aug is None else videos_t_aug
+    ks = keep_scales or {}
     with torch.no_grad():
-        _, attn, img = teacher_forward(teacher_sd, videos_t, tcfg, return_cls=True)            # :434-451 (attn only is used)
+        _, attn, img = teacher_forward(teacher_sd, v_mask, tcfg, return_cls=True)              # :434-451 (attn only is used)
+        if videos_t_aug is not None:
+            _, _, img = teacher_forward(teacher_sd, videos_t, tcfg, return_cls=True)            # clip_infer sees videos_t (:557)
     params = {k_: v.detach().clone().requires_grad_(with_grads) for k_, v in student_sd.items()}
     full_s = torch.zeros(Bs, scfg.num_patches, dtype=torch.bool)
     full_t = torch.zeros(Bt, scfg.num_patches, dtype=torch.bool)
-    enc_s, _ = student_forward(params, videos_s, full_s, scfg, clip_only=False)                 # :475
+    enc_s, _ = student_forward(params, videos_s, full_s, scfg, clip_only=False, keep_scales=ks.get("s"))   # :475
     logits_s = F.linear(pool_outputs(enc_s), cls_w, cls_b)                                      # :476-477
     with torch.no_grad():
-        enc_t, _ = student_forward(params, videos_t, full_t, scfg, clip_only=False)             # :480-481
+        enc_t, _ = student_forward(params, videos_t, full_t, scfg, clip_only=False, keep_scales=ks.get("t"))   # :480-481
         logits_full_t = F.linear(pool_outputs(enc_t), cls_w, cls_b)                             # :482-483
     loss_s = F.cross_entropy(logits_s, labels_s)                                                # :486
     gm = greedy_masks(attn, mask_ratio, k)                                                      # :496
     T = attn.shape[0] // Bt
     masks = gm.reshape(k, Bt, T * attn.shape[1]).reshape(k * Bt, -1)                            # 'k (B T) N -> (k B) (T N)'  :497
-    videos_tk = videos_t.repeat(k, 1, 1, 1, 1)                                                  # :499
-    enc_m, _ = student_forward(params, videos_tk, masks, scfg, clip_only=False)                 # :502
+    videos_tk = v_mask.repeat(k, 1, 1, 1, 1)                                                    # :499
+    enc_m, _ = student_forward(params, videos_tk, masks, scfg, clip_only=False, keep_scales=ks.get("m"))   # :502
     logits_masked = F.linear(pool_outputs(enc_m), cls_w, cls_b).reshape(k, Bt, -1)              # :503-505
     clip_probs = clip_zero_shot(img, text_features, Bt)                                         # :557
     fus = pseudo_label_fusion(logits_full_t, logits_masked, clip_probs, clip_threshold, tgt_ratio)

@@ -15,7 +15,7 @@ student, teacher = bench.build_models(seed=0)
 student, teacher = student.to(dev).train(), teacher.to(dev).eval()
 model = DataParallel(student); model.grad_sync = None
 eng = Stage1Engine(student, teacher, mask_ratio=0.8, use_graph=True)
-efp._ENGINES[(id(student), id(teacher))] = eng
+efp.register_engine(student, teacher, eng)
 loader = SyntheticStage1Loader(B, steps=20, seed=0, rank=0, n_distinct=2)
 
 class A: log_freq = 1; use_cuda_graph = True

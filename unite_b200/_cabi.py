@@ -65,8 +65,8 @@ SIGNATURES = {
     "ub_layernorm_fwd": (C.c_int, [_P, _I, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P]),
     "ub_teacher_embed_ln": (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _I, _P, _I, _I, _I, _P]),
     "ub_layernorm_bwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P]),
-    "ub_dec_tail_fwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _F, _I, _I, _P]),
-    "ub_dec_tail_bwd": (C.c_int, [_P, _P, _P, _F, _P, _F, _P, _P, _P, _I, _I, _P]),
+    "ub_dec_tail_fwd": (C.c_int, [_P, _P, _P, _F, _P, _P, _P, _F, _I, _I, _I, _I, _P]),
+    "ub_dec_tail_bwd": (C.c_int, [_P, _P, _P, _F, _P, _F, _I, _I, _P, _P, _P, _I, _I, _P]),
     "ub_l2norm_rows": (C.c_int, [_P, _I, _I, _P]),
     "ub_patchify": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "ub_patchify_u8": (C.c_int, [_P, _P, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _I, _I, _I, _I, _P]),
@@ -77,7 +77,10 @@ SIGNATURES = {
     "ub_sumsq": (C.c_int, [_P, _L, _P, _P]),
     "ub_adamw": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _F, _F, _F, _F, _F, _I, _F, _P]),
     "ub_adamw_dev": (C.c_int, [_P, _P, _P, _P, _P, _L, _L, _P, _P, _P]),
+    "ub_adamw_seg": (C.c_int, [_P, _P, _P, _P, _P, _L, _P, _I, _P, _P, _P]),
+    "ub_sumsq_seg": (C.c_int, [_P, _L, _P, _I, _P, _P, _P]),
     "ub_cast_bf16": (C.c_int, [_P, _P, _L, _P]),
+    "ub_drop_path_draw": (C.c_int, [_P, _P, _I, _I, C.c_uint64, _P, _P]),
     "ub_nvls_slots": (C.c_int, []),
     "ub_adamw_nvls": (C.c_int, [_P, _P, _P, _P, _P, _P, _L, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ub_meanpool_fwd": (C.c_int, [_P, _P, _I, _I, _I, _P]),

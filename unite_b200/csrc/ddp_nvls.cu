@@ -59,17 +59,21 @@ UB_DEVINL uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// spin until *slot >= target (wrap-safe); gives up after `limit` clocks and records the failure
-UB_DEVINL void wait_ge(const uint32_t* slot, uint32_t target, long long limit, int* err, int code) {
+// spin until *slot >= target (wrap-safe); gives up after `limit` clocks, records the failure in *err (sticky: every later
+// launch returns at once, see nvls_dead) and returns false — the caller must then NOT touch parameters or optimizer state
+UB_DEVINL bool wait_ge(const uint32_t* slot, uint32_t target, long long limit, int* err, int code) {
   const long long t0 = clock64();
   while ((int32_t)(ld_acquire_sys_u32(slot) - target) < 0) {
-    if (clock64() - t0 > limit) {
-      atomicExch(err, code);
-      break;
+    if (clock64() - t0 > limit || *reinterpret_cast<volatile int*>(err) != 0) {
+      atomicCAS(err, 0, code);
+      return false;
     }
     __nanosleep(32);
   }
+  return true;
 }
+// a previous launch (or another CTA of this one) gave up on a barrier: the step is void, nothing may be updated any more
+UB_DEVINL bool nvls_dead(const int* err) { return *reinterpret_cast<const volatile int*>(err) != 0; }
 
 struct NvlsStep {
   float* p; const float* g_mc; float* m; float* v;
@@ -176,15 +180,22 @@ __global__ void __launch_bounds__(256) adamw_nvls_kernel(const NvlsStep a) {
   pdl_grid_sync();
   __shared__ float s_part[8];
   __shared__ uint32_t s_epoch;
+  __shared__ int s_abort;
   const int b = blockIdx.x, nb = gridDim.x;
   // ---- entry barrier: every rank's backward is complete, no rank still reads the previous shadow ----
   if (threadIdx.x == 0) {
-    const uint32_t e = a.epoch[b];
-    s_epoch = e;
-    mc_signal(a.flags_mc + b);
-    wait_ge(a.flags + b, (e + 1u) * (uint32_t)a.world, a.spin_limit, a.err, 1);
+    s_abort = 0;
+    if (nvls_dead(a.err)) {
+      s_abort = 1;
+    } else {
+      const uint32_t e = a.epoch[b];
+      s_epoch = e;
+      mc_signal(a.flags_mc + b);
+      if (!wait_ge(a.flags + b, (e + 1u) * (uint32_t)a.world, a.spin_limit, a.err, 1)) s_abort = 1;
+    }
   }
   __syncthreads();
+  if (s_abort) return;                   // a peer never arrived: applying AdamW to partial sums would silently diverge the ranks
   const float lr = a.hyper[0], wd = a.hyper[1], beta1 = a.hyper[2], beta2 = a.hyper[3], eps = a.hyper[4], bc1 = a.hyper[5],
               bc2_sqrt = a.hyper[6], grad_scale = a.hyper[7];
   const float step_size = lr / bc1;
@@ -227,14 +238,21 @@ __global__ void __launch_bounds__(256) adamw_push_kernel(const NvlsStep a) {
   pdl_grid_sync();
   __shared__ float s_part[8];
   __shared__ uint32_t s_epoch;
+  __shared__ int s_abort;
   const int b = blockIdx.x, nb = gridDim.x;
   if (threadIdx.x == 0) {
-    const uint32_t e = a.epoch[b];
-    s_epoch = e;
-    mc_signal(a.flags_mc + b);
-    wait_ge(a.flags + b, (e + 1u) * (uint32_t)kW, a.spin_limit, a.err, 1);
+    s_abort = 0;
+    if (nvls_dead(a.err)) {
+      s_abort = 1;
+    } else {
+      const uint32_t e = a.epoch[b];
+      s_epoch = e;
+      mc_signal(a.flags_mc + b);
+      if (!wait_ge(a.flags + b, (e + 1u) * (uint32_t)kW, a.spin_limit, a.err, 1)) s_abort = 1;
+    }
   }
   __syncthreads();
+  if (s_abort) return;                   // void step: no scatter, no update (see wait_ge)
   const long tid = (long)b * blockDim.x + threadIdx.x, stride = (long)nb * blockDim.x;
   const long shard = (a.n8_decay + kW - 1) / kW;
   const float4* g_local = reinterpret_cast<const float4*>(a.g_peer[a.rank]);
@@ -260,9 +278,10 @@ __global__ void __launch_bounds__(256) adamw_push_kernel(const NvlsStep a) {
   if (threadIdx.x == 0) {
     __threadfence_system();
     mc_signal(a.mid_mc);
-    wait_ge(a.mid, (s_epoch + 1u) * (uint32_t)(kW * nb), a.spin_limit, a.err, 3);
+    if (!wait_ge(a.mid, (s_epoch + 1u) * (uint32_t)(kW * nb), a.spin_limit, a.err, 3)) s_abort = 1;
   }
   __syncthreads();
+  if (s_abort) return;                   // some rank's gradients never arrived: leave p / m / v and the shadows alone
   // ---- phase B: reduce (local reads), AdamW on my slice, shadow to every rank ----
   const float lr = a.hyper[0], wd = a.hyper[1], beta1 = a.hyper[2], beta2 = a.hyper[3], eps = a.hyper[4], bc1 = a.hyper[5],
               bc2_sqrt = a.hyper[6], grad_scale = a.hyper[7];
@@ -343,7 +362,10 @@ extern "C" int ub_adamw_nvls(float* p, const float* g_mc, float* m, float* v, vo
   a.rank = rank; a.world = world;
   a.hyper = hyper; a.gnorm_mc = gnorm_sq_mc;
   a.flags = flags; a.flags_mc = flags_mc; a.epoch = epoch; a.err = err;
-  a.spin_limit = 60000000000LL;          // ~30 s of SM clocks: beyond any rank skew (a peer capturing its CUDA graph), then give up
+  // UB_NVLS_SPIN_S (default 120 s of SM clocks at ~1.9 GHz): beyond any legitimate rank skew (a peer capturing its CUDA graph,
+  // writing a checkpoint, a loader hiccup); past it the step is declared void on this rank (see wait_ge / nvls_dead)
+  static const long long spin_clocks = (long long)(env_int("UB_NVLS_SPIN_S", 120) > 0 ? env_int("UB_NVLS_SPIN_S", 120) : 120) * 1900000000LL;
+  a.spin_limit = spin_clocks;
   const bool p2p = g_peers != nullptr && !nvls_mode_mc() && (world == 2 || world == 4 || world == 8);
   for (int r = 0; r < 8; ++r) {
     a.g_peer[r] = p2p && r < world ? (const float*)g_peers[r] : nullptr;

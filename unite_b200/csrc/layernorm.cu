@@ -316,7 +316,8 @@ template <int NV>
 __global__ void __launch_bounds__(256) dec_tail_fwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float* __restrict__ out,
                                                            const float* __restrict__ tgt, float* __restrict__ loss_acc,
-                                                           float loss_scale, int rows, int D, float eps) {
+                                                           float loss_scale, int rows, int D, float eps, int loss_lo,
+                                                           int loss_hi) {
   pdl_grid_sync();
   __shared__ float s_loss[8];
   const int lane = threadIdx.x & 31;
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(256) dec_tail_fwd_kernel(const float* __restri
     const float inv = 1.0f / sqrtf(row_dot(x, x, nv));
     UB_ROW_FOREACH(i, nv) { x.v[i].x *= inv; x.v[i].y *= inv; x.v[i].z *= inv; x.v[i].w *= inv; }
     row_store_f32(x, out + (int64_t)row * D, nv, lane);
-    if (tgt) {
+    if (tgt && row >= loss_lo && row < loss_hi) {      // rows outside [loss_lo, loss_hi) do not enter the loss (clip_loss_data)
       RowT<NV> t;
       row_load_f32(t, tgt + (int64_t)row * D, nv, lane);
       lacc += 2.0f - 2.0f * row_dot(x, t, nv);
@@ -363,7 +364,8 @@ template <int NV>
 __global__ void __launch_bounds__(256) dec_tail_bwd_kernel(const float* __restrict__ y, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, const float* __restrict__ go,
                                                            float go_scale, bf16* __restrict__ dy_out, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta, int rows, int D, float eps) {
+                                                           float* __restrict__ dbeta, int rows, int D, float eps, int go_lo,
+                                                           int go_hi) {
   pdl_grid_sync();
   extern __shared__ float s_red[];
   const int lane = threadIdx.x & 31;
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(256) dec_tail_bwd_kernel(const float* __restri
     }
     const float inv = 1.0f / sqrtf(row_dot(u, u, nv));
     const float ug = row_dot(u, du, nv) * inv * inv;     // <out, go> / ||u||  (still unscaled by go_scale)
-    const float k = go_scale * inv;
+    const float k = (row >= go_lo && row < go_hi) ? go_scale * inv : 0.f;   // rows outside the range received no gradient
     float s1 = 0.f, s2 = 0.f;
     UB_ROW_FOREACH(i, nv) {
       // du <- go_scale * (go - out*<out,go>) / ||u||
@@ -506,20 +508,27 @@ extern "C" int ub_layernorm_bwd(const void* dy, const float* x, const float* gam
 }
 
 extern "C" int ub_dec_tail_fwd(const float* y, const float* gamma, const float* beta, float eps, float* out,
-                               const float* tgt, float* loss_acc, float loss_scale, int rows, int D, void* stream) {
+                               const float* tgt, float* loss_acc, float loss_scale, int loss_row_lo, int loss_row_hi, int rows, int D,
+                               void* stream) {
   UB_REQUIRE(y && gamma && beta && out, "dec_tail_fwd: null pointer");
   UB_REQUIRE((tgt == nullptr) || (loss_acc != nullptr), "dec_tail_fwd: tgt needs loss_acc");
+  UB_REQUIRE(loss_row_lo >= 0 && loss_row_lo <= loss_row_hi && loss_row_hi <= rows, "dec_tail_fwd: loss rows [%d, %d) of %d", loss_row_lo,
+             loss_row_hi, rows);
   if (check_D(D, "dec_tail_fwd")) return 1;
-  UB_LN_DISPATCH(D, dec_tail_fwd_kernel, ln_grid(rows), 0, (cudaStream_t)stream, y, gamma, beta, out, tgt, loss_acc, loss_scale, rows, D, eps)
+  UB_LN_DISPATCH(D, dec_tail_fwd_kernel, ln_grid(rows), 0, (cudaStream_t)stream, y, gamma, beta, out, tgt, loss_acc, loss_scale, rows, D, eps,
+                 loss_row_lo, loss_row_hi)
   return check_launch("dec_tail_fwd_kernel");
 }
 
 extern "C" int ub_dec_tail_bwd(const float* y, const float* gamma, const float* beta, float eps, const float* go,
-                               float go_scale, void* dy_out, float* dgamma, float* dbeta, int rows, int D, void* stream) {
+                               float go_scale, int go_row_lo, int go_row_hi, void* dy_out, float* dgamma, float* dbeta, int rows,
+                               int D, void* stream) {
   UB_REQUIRE(y && gamma && beta && go && dy_out && dgamma && dbeta, "dec_tail_bwd: null pointer");
+  UB_REQUIRE(go_row_lo >= 0 && go_row_lo <= go_row_hi && go_row_hi <= rows, "dec_tail_bwd: gradient rows [%d, %d) of %d", go_row_lo,
+             go_row_hi, rows);
   if (check_D(D, "dec_tail_bwd")) return 1;
   UB_LN_DISPATCH(D, dec_tail_bwd_kernel, ln_bwd_grid(rows), 8 * D * sizeof(float), (cudaStream_t)stream, y, gamma, beta, go, go_scale,
-                 (bf16*)dy_out, dgamma, dbeta, rows, D, eps)
+                 (bf16*)dy_out, dgamma, dbeta, rows, D, eps, go_row_lo, go_row_hi)
   return check_launch("dec_tail_bwd_kernel");
 }
 

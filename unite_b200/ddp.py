@@ -84,6 +84,9 @@ class NvlsShardedStep:
     def __init__(self, arena, optimizer, process_group=None):
         import torch.distributed._symmetric_memory as symm
         from . import _cabi
+        if not getattr(optimizer, "plain_two_groups", True):
+            raise NotImplementedError("ub_adamw_nvls updates the plain [decay | no-decay] arena layout; layer-decay groups or frozen "
+                                      "parameters need the NCCL path (UB_DDP_NVLS=0)")
         self.arena, self.opt = arena, optimizer
         self.pg = process_group if process_group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.pg), dist.get_world_size(self.pg)
@@ -143,11 +146,45 @@ class NvlsShardedStep:
                        o._hyper_dev, self.gnorm_mc, self.flags, self.flags_mc, self._epoch, self._err, self.g_peers, self.w16_peers, self.stage_peers)
         self.calls += 1
 
+    def step_dev_clipped(self, max_norm: float):
+        """clip_grad with the fused step (loss_scaler(..., clip_grad=max_norm), utils.py:613-615): the clip coefficient needs the
+        norm of the SUMMED gradient before any update, which the one-pass kernel cannot know.  So the sum is formed first (one
+        NCCL all-reduce of the symmetric gradient arena, in place), its norm measured, and the fused kernel then runs on N
+        identical copies: it adds them up again (exactly N x for N a power of two), which the 1/N^2 in grad_scale undoes.
+        Slower than the unclipped step by one all-reduce; clip_grad is null in every shipped config."""
+        from . import ops
+        a, o = self.arena, self.opt
+        dist.all_reduce(a.grads, op=dist.ReduceOp.SUM, group=self.pg)
+        if not hasattr(self, "_clip_sq"):
+            self._clip_sq = torch.zeros(1, device=a.device, dtype=torch.float32)
+            self._hyper_clip = torch.zeros_like(o._hyper_dev)
+        self._clip_sq.zero_()
+        ops.sumsq(a.grads, self._clip_sq)
+        h = self._hyper_clip
+        h.copy_(o._hyper_dev)
+        norm = self._clip_sq.sqrt() / self.world                              # norm of the rank-averaged gradient
+        h[7:8] = (max_norm / (norm + 1e-6)).clamp(max=1.0) / float(self.world * self.world)
+        ops.adamw_nvls(a.params, self.g_mc, o.exp_avg, o.exp_avg_sq, a.w16, self.w16_mc, a.n_decay, self.rank, self.world,
+                       h, None, self.flags, self.flags_mc, self._epoch, self._err, self.g_peers, self.w16_peers, self.stage_peers)
+        o.gnorm_sq.copy_(self._clip_sq)                                        # grad_norm(1/world) then reports the pre-clip norm
+        self.calls += 1
+
+    _ERR_NAMES = {1: "entry", 2: "exit", 3: "mid"}
+
+    def raise_if(self, code: int):
+        if code:
+            raise RuntimeError(f"ub_adamw_nvls (rank {self.rank}): a peer never reached the {self._ERR_NAMES.get(code, code)} barrier "
+                               "within UB_NVLS_SPIN_S seconds; the step was declared void and no later step updates anything — "
+                               "the run must stop (the other ranks time out on their next step and raise the same error)")
+
     def check(self):
         """Host-side health check (syncs): raises if a peer ever missed a barrier inside the kernel."""
-        code = int(self._err.item())
-        if code:
-            raise RuntimeError(f"ub_adamw_nvls: a peer never reached the {'entry' if code == 1 else 'exit'} barrier (rank {self.rank})")
+        self.raise_if(int(self._err.item()))
+
+    def poll_error_async(self, pinned_int32: torch.Tensor):
+        """Enqueue a 4-byte D2H copy of the error word (the training loops do it next to their loss read-back, then call
+        raise_if() on the value once the copy's event has completed — no extra synchronisation)."""
+        pinned_int32.copy_(self._err, non_blocking=True)
 
     def consolidate(self):
         """Gather the sharded fp32 master weights and Adam moments so that every rank holds all of them."""

@@ -19,74 +19,166 @@ import torch
 
 from . import ops
 from .modeling_adaptation import AdaptationVisionTransformer
-from .modeling_finetune import drop_path_factors
 from .clip import VisionTransformer as ClipVisionTransformer
 
 BF16, F32, I32, U8 = torch.bfloat16, torch.float32, torch.int32, torch.uint8
 
 
-class FusedAdamW:
-    """AdamW over a ParamArena (two groups: decay / no-decay), one kernel per step; also refreshes the bf16
-    weight shadow and measures the global gradient norm (utils.py:631-643) without per-tensor kernels."""
+def get_num_layer_for_vit(var_name: str, num_max_layer: int) -> int:
+    """Layer id of a parameter for layer-wise lr decay — src/optim_factory.py:45-63 (note: names are matched WITHOUT stripping a
+    wrapper prefix, so every `encoder.*` parameter of the adaptation student lands in the last group, as in the reference)."""
+    if var_name in ("cls_token", "mask_token", "pos_embed"):
+        return 0
+    if var_name.startswith("patch_embed"):
+        return 0
+    if var_name.startswith("rel_pos_bias"):
+        return num_max_layer - 1
+    if var_name.startswith("blocks"):
+        return int(var_name.split(".")[1]) + 1
+    if var_name.startswith("transformer.resblocks"):
+        return int(var_name.split(".")[2]) + 1
+    if var_name in ("class_embedding", "positional_embedding", "temporal_positional_embedding"):
+        return 0
+    if var_name.startswith("conv1"):
+        return 0
+    return num_max_layer - 1
 
-    def __init__(self, arena, lr=1.5e-4, weight_decay=0.05, betas=(0.9, 0.95), eps=1e-8):
+
+class LayerDecayValueAssigner:
+    """src/optim_factory.py:66-74; built as run_stage2.py:616-617 does: values = [decay ** (L + 1 - i) for i in range(L + 2)]."""
+
+    def __init__(self, values):
+        self.values = list(values)
+
+    def get_scale(self, layer_id):
+        return self.values[layer_id]
+
+    def get_layer_id(self, var_name):
+        return get_num_layer_for_vit(var_name, len(self.values))
+
+
+class FusedAdamW:
+    """AdamW over a ParamArena, one kernel per step (ub_adamw_seg); also refreshes the bf16 weight shadow and measures the global
+    gradient norm (utils.py:631-643) without per-tensor kernels.
+
+    Parameter groups follow src/optim_factory.py:76-118 (get_parameter_groups): "decay" / "no_decay", or with a layer assigner
+    (get_num_layer / get_layer_scale, optim_factory.py:66-74) "layer_%d_decay" / "layer_%d_no_decay" with their `lr_scale`;
+    parameters with requires_grad=False at construction are left out of every group (:83-84) and are never touched.  Each group
+    is one or more contiguous runs of the arena; `param_groups` holds one dict per group exactly like torch's, and the training
+    loops write `lr` / `weight_decay` into them every step (run_stage1.py:326-338, engine_for_finetuning.py:76-81)."""
+
+    def __init__(self, arena, lr=1.5e-4, weight_decay=0.05, betas=(0.9, 0.95), eps=1e-8, get_num_layer=None, get_layer_scale=None):
         self.arena = arena
         self.lr, self.weight_decay, self.betas, self.eps = lr, weight_decay, betas, eps
         self.exp_avg = torch.zeros_like(arena.params)
         self.exp_avg_sq = torch.zeros_like(arena.params)
         self.step_count = 0
         self.gnorm_sq = torch.zeros(1, device=arena.device, dtype=F32)
-        # the reference writes lr / weight_decay into these every step (run_stage1.py:326-338)
-        self.param_groups = [dict(name="decay", lr=lr, weight_decay=weight_decay, lr_scale=1.0),
-                             dict(name="no_decay", lr=lr, weight_decay=0.0, lr_scale=1.0)]
+        # ---- groups and their runs in the arena ---------------------------------------------------------------------------
+        self.param_groups, index = [], {}
+        seg_group, seg_end = [], []
+        for i, name in enumerate(arena.names):
+            off, numel = arena.offsets[name]
+            p = arena._params[name]
+            nxt = arena.offsets[arena.names[i + 1]][0] if i + 1 < len(arena.names) else arena.numel
+            if not p.requires_grad:
+                gi = -1                                                         # frozen: optim_factory.py:83-84
+            else:
+                decay = off < arena.n_decay
+                gname = "decay" if decay else "no_decay"
+                scale = 1.0
+                if get_num_layer is not None:
+                    layer_id = get_num_layer(name)
+                    gname = "layer_%d_%s" % (layer_id, gname)
+                    if get_layer_scale is not None:
+                        scale = float(get_layer_scale(layer_id))
+                if gname not in index:
+                    index[gname] = len(self.param_groups)
+                    self.param_groups.append(dict(name=gname, lr=lr * scale, weight_decay=weight_decay if decay else 0.0,
+                                                  lr_scale=scale, params=[]))
+                gi = index[gname]
+                self.param_groups[gi]["params"].append(p)
+            if seg_group and seg_group[-1] == gi:
+                seg_end[-1] = nxt
+            else:
+                seg_group.append(gi)
+                seg_end.append(nxt)
+        if any(e % 4 for e in seg_end):
+            raise RuntimeError("arena parameter offsets must be multiples of 4 elements")
+        if not self.param_groups:
+            raise ValueError("FusedAdamW: every parameter is frozen")
+        self._seg_group = seg_group
+        self._seg_end4 = torch.tensor([e // 4 for e in seg_end], dtype=I32, device=arena.device)
+        self.n_seg = len(seg_group)
+        # the two-group default layout [decay | no-decay] without frozen parameters is what the fused NVLink step understands
+        self.plain_two_groups = [g["name"] for g in self.param_groups] in (["decay", "no_decay"], ["decay"]) and \
+            -1 not in seg_group and self.n_seg == len(self.param_groups)
+        n_h = 8 + 2 * self.n_seg
+        self._hyper_dev = torch.zeros(n_h, device=arena.device, dtype=F32)
+        self._hyper_pin = None
+        self._hyper_ev = None
 
     def zero_grad(self, set_to_none: bool = False):
         self.arena.grads.zero_()
 
-    # ---- graph-friendly form: scalars live in device memory, refreshed by one 32-byte async copy per step ----------
+    # ---- graph-friendly form: scalars live in device memory, refreshed by one small async copy per step ----------------------
+    _RING = 8
+
     def prepare_step(self, grad_scale: float = 1.0):
-        """Host side of a (possibly graph-replayed) step: advance the step counter and upload lr / wd / bias corrections."""
-        if not hasattr(self, "_hyper_dev"):
-            self._hyper_dev = torch.zeros(8, device=self.arena.device, dtype=F32)
-            self._hyper_pin = [torch.zeros(8, dtype=F32).pin_memory() for _ in range(4)]
+        """Host side of a (possibly graph-replayed) step: advance the step counter and upload every group's lr / wd and the bias
+        corrections.  The upload goes through a ring of pinned slots; a slot is rewritten only after the copy that last read
+        it has EXECUTED (an event per slot) — the DMA reads pinned memory when it runs, not when it is enqueued, and a host
+        that queues graph replays can be many steps ahead of the device."""
+        on_gpu = self._hyper_dev.is_cuda
+        if self._hyper_pin is None:
+            self._hyper_pin = [torch.zeros_like(self._hyper_dev, device="cpu").pin_memory() if on_gpu else
+                               torch.zeros_like(self._hyper_dev, device="cpu") for _ in range(self._RING)]
+            self._hyper_ev = [None] * self._RING
         self.step_count += 1
-        g0 = self.param_groups[0]
         b1, b2 = self.betas
-        hp = self._hyper_pin[self.step_count % 4]
-        hp.copy_(torch.tensor([g0["lr"], g0["weight_decay"], b1, b2, self.eps, 1.0 - b1 ** self.step_count,
-                               math.sqrt(1.0 - b2 ** self.step_count), grad_scale], dtype=F32))
+        k = self.step_count % self._RING
+        if self._hyper_ev[k] is not None:
+            self._hyper_ev[k].synchronize()
+        S = self.n_seg
+        vals = [0.0] * (8 + 2 * S)
+        g0 = self.param_groups[0]
+        vals[0], vals[1] = g0["lr"], g0["weight_decay"]                        # read by ub_adamw_nvls (plain two-group layout)
+        vals[2:8] = [b1, b2, self.eps, 1.0 - b1 ** self.step_count, math.sqrt(1.0 - b2 ** self.step_count), grad_scale]
+        for s, gi in enumerate(self._seg_group):
+            if gi < 0:
+                vals[8 + s], vals[8 + S + s] = 0.0, -1.0
+            else:
+                g = self.param_groups[gi]
+                vals[8 + s], vals[8 + S + s] = g["lr"], g["weight_decay"]
+        hp = self._hyper_pin[k]
+        hp.copy_(torch.tensor(vals, dtype=F32))
         self._hyper_dev.copy_(hp, non_blocking=True)
+        if on_gpu:
+            self._hyper_ev[k] = torch.cuda.Event()
+            self._hyper_ev[k].record()
 
     def step_dev(self, max_norm: Optional[float] = None):
         """Device side: grad-norm + AdamW reading the scalars uploaded by prepare_step (capturable in a CUDA graph).
         max_norm: utils.py:613-615 (torch.nn.utils.clip_grad_norm_ before the step): the norm must be known before the
-        update, so it takes its own sweep (ub_sumsq); the clip coefficient min(1, max_norm / (norm + 1e-6)) is folded into
+        update, so it takes its own sweep (ub_sumsq_seg); the clip coefficient min(1, max_norm / (norm + 1e-6)) is folded into
         the kernel's grad_scale on the device — no host read, the gradients themselves are not rewritten."""
         a = self.arena
         self.gnorm_sq.zero_()
         if not max_norm:
-            ops.adamw_dev(a.params, a.grads, self.exp_avg, self.exp_avg_sq, a.w16, a.n_decay, self._hyper_dev, self.gnorm_sq)
+            ops.adamw_seg(a.params, a.grads, self.exp_avg, self.exp_avg_sq, a.w16, self._seg_end4, self._hyper_dev, self.gnorm_sq)
             return
-        ops.sumsq(a.grads, self.gnorm_sq)
+        ops.sumsq_seg(a.grads, self._seg_end4, self._hyper_dev, self.gnorm_sq)
         if not hasattr(self, "_hyper_clip"):
             self._hyper_clip = torch.zeros_like(self._hyper_dev)
         h = self._hyper_clip
         h.copy_(self._hyper_dev)
         norm = self.gnorm_sq.sqrt() * self._hyper_dev[7:8]               # norm of the AVERAGED gradients (the arena holds rank sums)
         h[7:8] = self._hyper_dev[7:8] * (max_norm / (norm + 1e-6)).clamp(max=1.0)
-        ops.adamw_dev(a.params, a.grads, self.exp_avg, self.exp_avg_sq, a.w16, a.n_decay, h, None)
+        ops.adamw_seg(a.params, a.grads, self.exp_avg, self.exp_avg_sq, a.w16, self._seg_end4, h, None)
 
     def step(self, grad_scale: float = 1.0, max_norm: Optional[float] = None):
-        if max_norm:
-            self.prepare_step(grad_scale=grad_scale)
-            return self.step_dev(max_norm=max_norm)
-        a = self.arena
-        self.step_count += 1
-        self.gnorm_sq.zero_()
-        ops.sumsq(a.grads, self.gnorm_sq)
-        g0 = self.param_groups[0]
-        ops.adamw(a.params, a.grads, self.exp_avg, self.exp_avg_sq, a.w16, a.n_decay, g0["lr"], g0["weight_decay"], self.betas[0],
-                  self.betas[1], self.eps, self.step_count, grad_scale)
+        self.prepare_step(grad_scale=grad_scale)
+        self.step_dev(max_norm=max_norm)
 
     def consolidate(self):
         """Collective no-op unless the optimizer state is sharded by rank (ddp.NvlsShardedStep attaches itself as `_sharded`):
@@ -99,25 +191,46 @@ class FusedAdamW:
         return self.gnorm_sq.sqrt() * grad_scale
 
     def state_dict(self):
-        return dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, param_groups=self.param_groups)
+        groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
+        return dict(step=self.step_count, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, param_groups=groups)
 
     def load_state_dict(self, sd):
         self.step_count = sd["step"]
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        self.param_groups = sd["param_groups"]
+        if len(sd["param_groups"]) != len(self.param_groups):
+            raise ValueError("optimizer state has a different number of parameter groups")
+        for g, saved in zip(self.param_groups, sd["param_groups"]):
+            g.update({k: v for k, v in saved.items() if k != "params"})
+
+
+def require_fused_optimizer(optimizer, arena, what: str):
+    """The engines update the arena with FusedAdamW only.  A foreign optimizer (torch.optim.AdamW from the reference's
+    create_optimizer, src/optim_factory.py:120-175) would silently be ignored — refuse it instead."""
+    if optimizer is None:
+        return None
+    if not isinstance(optimizer, FusedAdamW):
+        raise TypeError(f"{what}: optimizer must be a unite_b200 FusedAdamW built over the model's parameter arena (see "
+                        f"unite_b200.optim_factory.create_optimizer), got {type(optimizer).__name__}; a torch optimizer cannot "
+                        "drive the fused step")
+    if optimizer.arena is not arena:
+        raise ValueError(f"{what}: the optimizer was built over a different parameter arena than this model's")
+    return optimizer
 
 
 class Stage1Engine:
     def __init__(self, student: AdaptationVisionTransformer, teacher: ClipVisionTransformer, mask_ratio: float = 0.8,
                  lr: float = 1.5e-4, weight_decay: float = 0.05, betas=(0.9, 0.95), eps: float = 1e-8, grad_sync=None,
-                 use_graph: bool = False, clip_loss_type: str = "l2"):
-        """use_graph: after two eager steps of a given batch shape, the whole step (teacher, mask, student fwd/bwd,
-        gradient all-reduce, grad-norm, AdamW) is captured once in a CUDA graph and replayed — the ~460 launches of a step
-        then cost one launch.  Requires DropPath off (random draws inside a captured region would be frozen)."""
+                 use_graph: bool = False, clip_loss_type: str = "l2", optimizer: Optional[FusedAdamW] = None):
+        """use_graph: after two eager steps of a given batch shape, the whole step (teacher, mask, DropPath draw, student
+        fwd/bwd, gradient all-reduce, grad-norm, AdamW) is captured once in a CUDA graph and replayed — the ~460 launches of a
+        step then cost one launch.  DropPath (drop_path: 0.1 in every shipped config) stays inside the graph: its factors come
+        from ub_drop_path_draw, a counter-based generator whose step counter lives in device memory (csrc/rng.cu)."""
         self.student, self.teacher, self.mask_ratio = student, teacher, mask_ratio
         self.use_graph = use_graph
         self.clip_loss_type = clip_loss_type
+        self.clip_loss_data = "mixed"         # 'source' / 'target': only the first B_s / the remaining clips enter the loss (:418-423)
+        self.n_source = None                  # B_s of the current batch (needed when clip_loss_data != 'mixed')
         self.max_norm = None                  # clip_grad of the reference's loss_scaler call (run_stage1.py:451-455); None / 0 = off
         self._graphs = {}
         self._graph_count, self._graph_pool = {}, None
@@ -125,13 +238,14 @@ class Stage1Engine:
         self._eager_steps = {}
         self.core = student.core()
         self.core.sync_shadow(force=True)
-        self.optimizer = FusedAdamW(self.core.arena, lr, weight_decay, betas, eps)
+        self.optimizer = require_fused_optimizer(optimizer, self.core.arena, "Stage1Engine") or \
+            FusedAdamW(self.core.arena, lr, weight_decay, betas, eps)
         self.grad_sync = grad_sync            # unite_b200.ddp.GradSync or None
         # N > 1: the all-reduce -> AdamW pair becomes ONE kernel over NVSwitch multicast (ddp.NvlsShardedStep) when the box
         # offers it; UB_DDP_NVLS=0 (or a box without multicast) keeps NCCL range all-reduces overlapped with backward
         self.nvls = None
         if grad_sync is not None and getattr(grad_sync, "world", 1) > 1 and self.core.arena.device.type == "cuda" \
-                and os.environ.get("UB_DDP_NVLS", "1") != "0":
+                and os.environ.get("UB_DDP_NVLS", "1") != "0" and self.optimizer.plain_two_groups:
             from .ddp import NvlsShardedStep
             try:
                 self.nvls = NvlsShardedStep(self.core.arena, self.optimizer, grad_sync.pg)
@@ -143,15 +257,18 @@ class Stage1Engine:
         self.share_patches = student.encoder.patch_embed.tubelet_size == teacher.kernel_size
         self.loss = torch.zeros(1, device=self.core.arena.device, dtype=F32)
         self.last = {}
+        self.drop_path = self.core.drop_path       # vit_core.DropPathSource: device-side draws, one launch per step
 
     def set_optimizer(self, optimizer: "FusedAdamW"):
         """Swap in a caller-built FusedAdamW over the same arena (train_one_epoch's `optimizer` argument); the fused data-parallel
         step, if active, is re-bound to it (its gradient-norm accumulator lives in symmetric memory)."""
         if optimizer is self.optimizer:
             return
-        if optimizer.arena is not self.core.arena:
-            raise ValueError("the optimizer was built over a different parameter arena than this engine's student")
+        require_fused_optimizer(optimizer, self.core.arena, "Stage1Engine.set_optimizer")
         if self.nvls is not None:
+            if not optimizer.plain_two_groups:
+                raise NotImplementedError("the fused NVLink step updates the plain [decay | no-decay] layout; layer-decay groups or "
+                                          "frozen parameters need UB_DDP_NVLS=0 (NCCL all-reduce + ub_adamw_seg)")
             self.nvls.opt = optimizer
             optimizer.gnorm_sq = self.optimizer.gnorm_sq
             optimizer._sharded = self.nvls
@@ -207,7 +324,8 @@ class Stage1Engine:
         mask, vis_idx, tea_rows = sel["mask"], sel["vis_idx"], sel["tea_rows"]
         targets = teacher.project_rows(layers, tea_rows.view(-1))                 # [K, B*Nv, C]
         if dp is None and self.student.training:
-            dp = drop_path_factors(self.student.encoder.drop_path_rates, B, videos.device)
+            dp = self.drop_path.draw(B)                                            # None when every rate is 0
+        loss_clips = self._loss_clips(B)
         self.loss.zero_()
         if patches_s is None:
             patches_s = patches if self.share_patches else None
@@ -215,14 +333,21 @@ class Stage1Engine:
         if kind == "l2":
             # shipped config: the loss and its gradient are fused into the decoder-tail kernels
             _, x_clip, state = core.run_forward(videos, vis_idx[0], patches_s, dp, True, True,
-                                                targets=targets, loss_acc=self.loss)
+                                                targets=targets, loss_acc=self.loss, loss_clips=loss_clips)
             core.run_backward(state, targets=targets, grad_sync=None if self.nvls is not None else self.grad_sync)
         else:
             # run_stage1.py:403-408,432-433 (nn.MSELoss / nn.SmoothL1Loss / nn.L1Loss, mean reduction): loss value and
             # d loss / d outputs are a few element-wise device ops on the [K,B,Nv,C] outputs; the rest of backward is shared
             _, x_clip, state = core.run_forward(videos, vis_idx[0], patches_s, dp, True, True)
             d = x_clip - targets.view_as(x_clip)
-            n = d.numel()
+            if loss_clips is not None:                                             # :418-423: slice both tensors along the clip axis
+                keep = torch.zeros(1, B, 1, 1, device=d.device, dtype=d.dtype)
+                keep[:, loss_clips[0]:loss_clips[1]] = 1.0
+                d = d * keep
+                n = d[:, loss_clips[0]:loss_clips[1]].numel()
+            else:
+                keep = None
+                n = d.numel()
             if kind == "mse":
                 self.loss += (d * d).sum() / n
                 g = d * (2.0 / n)
@@ -232,45 +357,59 @@ class Stage1Engine:
                 g = d.clamp(-1.0, 1.0) / n
             elif kind == "l1":
                 self.loss += d.abs().sum() / n
-                g = d.sign() / n
+                g = d.sign() / n                                                   # sign(0) = 0 on the rows outside the slice
             else:
                 raise NotImplementedError(f"clip_loss_type={kind!r} (run_stage1.py:430-435 raises for anything else too)")
             core.run_backward(state, g_clip=g, grad_sync=None if self.nvls is not None else self.grad_sync)
         self.last = dict(attn=attn, mask=mask.view(B, Tp * P).bool(), vis_idx=vis_idx[0], targets=targets, outputs=x_clip)
         return self.loss
 
+    def _loss_clips(self, B):
+        """Clip range [lo, hi) of the batch that enters the alignment loss (run_stage1.py:418-423); None = all ('mixed')."""
+        if self.clip_loss_data == "mixed":
+            return None
+        if self.clip_loss_data not in ("source", "target"):
+            raise NotImplementedError(f"clip_loss_data={self.clip_loss_data!r}")   # run_stage1.py:426-427
+        if self.n_source is None or not (0 <= self.n_source <= B):
+            raise ValueError(f"clip_loss_data={self.clip_loss_data!r} needs n_source (B_s, the number of source clips leading the "
+                             f"batch) in [0, {B}]")
+        lo, hi = (0, self.n_source) if self.clip_loss_data == "source" else (self.n_source, B)
+        if hi <= lo:
+            raise ValueError(f"clip_loss_data={self.clip_loss_data!r} selects no clip (B_s={self.n_source}, B={B})")
+        return lo, hi
+
     def _step_body_dev(self, videos, q):
         self.optimizer.zero_grad()
         self.forward_backward(videos, q, None)
         if self.nvls is not None:
-            self._no_clip_with_nvls()
-            self.nvls.step_dev()                        # reduce-scatter + AdamW + shadow all-gather, one kernel
+            if self.max_norm:
+                self.nvls.step_dev_clipped(self.max_norm)
+            else:
+                self.nvls.step_dev()                    # reduce-scatter + AdamW + shadow all-gather, one kernel
             return
         if self.grad_sync is not None:
             self.grad_sync.all_reduce(self.core.arena.grads)
         self.optimizer.step_dev(max_norm=self.max_norm)
 
-    def _no_clip_with_nvls(self):
-        if self.max_norm:
-            raise NotImplementedError("clip_grad needs the norm of the SUMMED gradient before the update; the fused NVLink step "
-                                      "reduces and updates in one pass — run with UB_DDP_NVLS=0 when clipping")
-
     def step(self, videos, q, dp=None):
-        graphable = self.use_graph and dp is None and not (self.student.training and any(r > 0 for r in self.student.encoder.drop_path_rates))
+        graphable = self.use_graph and dp is None
         if not graphable:
             self.optimizer.zero_grad()
             loss = self.forward_backward(videos, q, dp)
             if self.nvls is not None:
-                self._no_clip_with_nvls()
                 self.optimizer.prepare_step(grad_scale=1.0 / self.nvls.world)
-                self.nvls.step_dev()
+                if self.max_norm:
+                    self.nvls.step_dev_clipped(self.max_norm)
+                else:
+                    self.nvls.step_dev()
                 return loss
             scale = 1.0
             if self.grad_sync is not None:
                 scale = self.grad_sync.all_reduce(self.core.arena.grads)
             self.optimizer.step(grad_scale=scale, max_norm=self.max_norm)
             return loss
-        shape_key = (tuple(videos.shape), videos.dtype, tuple(q.shape), self.clip_loss_type, float(self.max_norm or 0.0))
+        shape_key = (tuple(videos.shape), videos.dtype, tuple(q.shape), self.clip_loss_type, float(self.max_norm or 0.0),
+                     self.clip_loss_data, self.n_source if self.clip_loss_data != "mixed" else None, bool(self.student.training))
         scale = 1.0 / self.grad_sync.world if self.grad_sync is not None else 1.0
         self.optimizer.prepare_step(grad_scale=scale)
         n = self._eager_steps.get(shape_key, 0)

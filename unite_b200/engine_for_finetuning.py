@@ -13,25 +13,32 @@ from typing import Iterable, Optional
 import torch
 
 from . import ops
-from .engine import FusedAdamW
-
-_OPT = {}
+from .engine import FusedAdamW, require_fused_optimizer
 
 
-def train_class_batch(model, samples, target, criterion=None):
-    """engine_for_finetuning.py:37-40 on the fused path: returns (device loss [1], logits) with gradients already
-    accumulated in the arena (scale folded in by the caller through `loss_scale`)."""
-    raise NotImplementedError("use train_one_epoch / finetune_step; the fused path computes loss and gradient together")
+def train_class_batch(model, samples, target, criterion):
+    """engine_for_finetuning.py:37-40, as written there: the model's forward is one autograd node over the fused kernels
+    (finetune_core._FinetuneFn), so `loss.backward()` on the returned loss accumulates into the parameter arena like any
+    torch module.  train_one_epoch below uses the fused loss+gradient kernel instead (no autograd, no host sync)."""
+    outputs = model(samples)
+    loss = criterion(outputs, target)
+    return loss, outputs
+
+
+def _default_optimizer(net):
+    """Only when the caller passes optimizer=None: one FusedAdamW per model, kept on the model object."""
+    opt = net.__dict__.get("_ub_default_optimizer")
+    if opt is None:
+        opt = FusedAdamW(net.core().arena, lr=1e-3, weight_decay=0.05, betas=(0.9, 0.999))
+        net.__dict__["_ub_default_optimizer"] = opt
+    return opt
 
 
 def finetune_step(model, samples, targets, loss_acc, scale=1.0):
     """One micro-step: forward, CE, backward.  Adds scale * mean CE to loss_acc (fp32 [1]).  Returns logits."""
     net = model.module if hasattr(model, "module") else model
     core = net.core()
-    dp = None
-    if net.training:
-        from .modeling_finetune import drop_path_factors
-        dp = drop_path_factors(net.drop_path_rates, samples.shape[0], samples.device)
+    dp = core.drop_path.draw(samples.shape[0]) if net.training else None       # modeling_finetune.py:42-50 (device-side draws)
     logits, state = core.run_forward(samples, dp, save=True)
     B = logits.shape[0]
     dlogits = torch.empty_like(logits)
@@ -46,21 +53,24 @@ def train_one_epoch(model: torch.nn.Module, criterion=None, data_loader: Iterabl
                     num_epochs=None, train_head_only=False, wandb_run=None, args=None):
     if mixup_fn is not None or model_ema is not None or train_head_only:
         raise NotImplementedError("mixup / EMA / head-only training are off in the shipped stage-2 config")
-    if max_norm:
-        raise NotImplementedError("clip_grad is null in every shipped config")
+    if criterion is not None and not (isinstance(criterion, torch.nn.CrossEntropyLoss) and criterion.label_smoothing == 0.0
+                                      and criterion.weight is None and criterion.reduction == "mean"):
+        raise NotImplementedError("the fused stage-2 loss is nn.CrossEntropyLoss() (run_stage2.py:702 without mixup / smoothing)")
     model.train(True)
     net = model.module if hasattr(model, "module") else model
     core = net.core()
     dev = core.arena.device
     update_freq = update_freq or 1
     start_steps = start_steps or 0
-    if optimizer is None or not hasattr(optimizer, "arena"):
-        optimizer = _OPT.setdefault(id(net), FusedAdamW(core.arena, lr=1e-3, weight_decay=0.05, betas=(0.9, 0.999)))
+    optimizer = require_fused_optimizer(optimizer, core.arena, "train_one_epoch") or _default_optimizer(net)
     gs = getattr(model, "grad_sync", None)
     loss_sum = torch.zeros(1, device=dev)
     loss_acc = torch.zeros(1, device=dev)
     correct = torch.zeros(1, device=dev)
+    gn_sum = torch.zeros(1, device=dev)
     seen = 0
+    n_updates = 0
+    data_iter_step = -1
     optimizer.zero_grad()
     for data_iter_step, batch in enumerate(data_loader):
         samples, targets = batch[0], batch[1]
@@ -81,16 +91,19 @@ def train_one_epoch(model: torch.nn.Module, criterion=None, data_loader: Iterabl
         seen += samples.shape[0]
         if (data_iter_step + 1) % update_freq == 0:
             scale = gs.all_reduce(core.arena.grads) if gs is not None else 1.0
-            optimizer.step(grad_scale=scale)
+            optimizer.step(grad_scale=scale, max_norm=float(max_norm) if max_norm else None)   # loss_scaler(..., clip_grad=max_norm)
+            gn_sum += optimizer.grad_norm(scale)
+            n_updates += 1
             optimizer.zero_grad()
-    n = max(1, data_iter_step + 1 if seen else 1)
+    n = max(1, data_iter_step + 1)
     loss_avg = (loss_sum / n).item()
     if not math.isfinite(loss_avg):
         print("Loss is {}, stopping training".format(loss_avg))
         sys.exit(1)
     lrs = [g["lr"] for g in optimizer.param_groups]
+    wds = [g["weight_decay"] for g in optimizer.param_groups if g["weight_decay"] > 0]
     return {"loss": loss_avg, "class_acc": (correct / max(seen, 1)).item(), "loss_scale": 1.0, "lr": max(lrs), "min_lr": min(lrs),
-            "grad_norm": optimizer.grad_norm().item()}
+            "weight_decay": wds[0] if wds else None, "grad_norm": (gn_sum / max(1, n_updates)).item()}
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -12,24 +12,34 @@ from typing import Iterable, Optional
 
 import torch
 
-from .engine import Stage1Engine
+from .engine import Stage1Engine, require_fused_optimizer
 
-_ENGINES = {}
 _IO = {}          # per device: copy stream, device staging ring, pinned loss read-back slots
+
+
+def register_engine(student, teacher, engine):
+    """The engine of a (student, teacher) pair lives ON the student module (not in an id()-keyed global: ids are reused after
+    garbage collection), so it is dropped together with the model."""
+    student.__dict__["_ub_stage1_engine"] = (teacher, engine)
 
 
 def _engine_for(model, teacher_model, mask_ratio, optimizer, use_graph=False):
     student = model.module if hasattr(model, "module") else model
     teacher = teacher_model.module if hasattr(teacher_model, "module") else teacher_model
-    key = (id(student), id(teacher))
-    if key not in _ENGINES:
+    held = student.__dict__.get("_ub_stage1_engine")
+    if held is None or held[0] is not teacher:
         gs = getattr(model, "grad_sync", None)
         if gs is not None:
             gs.arena = student.core().arena
-        _ENGINES[key] = Stage1Engine(student, teacher, mask_ratio=mask_ratio, grad_sync=gs, use_graph=use_graph)
-        if optimizer is not None and hasattr(optimizer, "arena"):
-            _ENGINES[key].set_optimizer(optimizer)
-    return _ENGINES[key]
+        optimizer = require_fused_optimizer(optimizer, student.core().arena, "train_one_epoch")
+        eng = Stage1Engine(student, teacher, mask_ratio=mask_ratio, grad_sync=gs, use_graph=use_graph, optimizer=optimizer)
+        register_engine(student, teacher, eng)
+        return eng
+    eng = held[1]
+    if optimizer is not None:
+        eng.set_optimizer(require_fused_optimizer(optimizer, eng.core.arena, "train_one_epoch"))
+    eng.mask_ratio = mask_ratio
+    return eng
 
 
 def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_train_target: Optional[Iterable] = None,
@@ -37,16 +47,21 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
                     lr_scheduler=None, start_steps=0, lr_schedule_values=None, wd_schedule_values=None, src_classifier=None,
                     teacher_model=None, clip_input_resolution=224, clip_loss_type="l2", clip_loss_ratio=0.5,
                     mask_type="attention", mask_ratio=0.0, use_wandb=False, args=None):
-    if mask_type != "attention" or src_classifier is not None:
-        # (the reference itself only runs with mask_type='attention': run_stage1.py:378 reads `attn`, which the other mask
-        # types never define)
-        raise NotImplementedError("the fused stage-1 path covers mask_type='attention' without a source classifier "
-                                  "(configs/stage1_config.yaml)")
+    if mask_type != "attention":
+        # the reference itself only runs with mask_type='attention': run_stage1.py:378 reads `attn`, which the other mask
+        # types never define (NameError on the first step)
+        raise NotImplementedError("stage 1 runs with mask_type='attention' only (configs/stage1_config.yaml; run_stage1.py:378)")
+    # src_classifier: run_stage1.py:412-415 then calls model(videos, mask) without clip_only and discards the encoder output —
+    # the loss is loss_clip either way (:438), and clip_return_layers ends at the last block, so the compute is identical
+    clip_loss_data = getattr(args, "clip_loss_data", "mixed") if args is not None else "mixed"
+    if clip_loss_data not in ("source", "target", "mixed"):
+        raise NotImplementedError(f"clip_loss_data={clip_loss_data!r}")                  # run_stage1.py:426-427
     if clip_loss_type not in ("l2", "mse", "smooth_l1", "l1"):
         raise NotImplementedError(f"clip_loss_type={clip_loss_type!r}")                  # run_stage1.py:434-435
     model.train()
     eng = _engine_for(model, teacher_model, mask_ratio, optimizer, use_graph=bool(getattr(args, "use_cuda_graph", False)))
     eng.clip_loss_type = clip_loss_type
+    eng.clip_loss_data = clip_loss_data
     eng.max_norm = float(max_norm) if max_norm else None       # loss_scaler(..., clip_grad=max_norm, ...), run_stage1.py:451-455
     opt = eng.optimizer
     dev = eng.core.arena.device
@@ -63,6 +78,7 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
                                   pin_loss=[torch.empty(1, pin_memory=True) for _ in range(2)]))
     copy_stream = io["stream"]           # persistent: the caching allocator keeps one pool per stream
     pin_loss = io["pin_loss"]
+    pin_err = io.setdefault("pin_err", [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(2)])
     loss_ev = [None, None]
     # Device staging ring (3 slots per tensor shape): allocating a fresh 154 MB tensor per step on the copy stream makes the
     # caching allocator cudaMalloc (a device-wide sync) whenever record_stream delays a block's reuse — measured as steps of
@@ -83,6 +99,7 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
 
     def fetch(batch):
         videos, noise = batch[0], (batch[3] if len(batch) > 3 else None)
+        n_source = videos.shape[0]                                             # B_s, run_stage1.py:342
         nonlocal it_target
         if it_target is not None:                                              # run_stage1.py:343-347
             try:
@@ -99,7 +116,7 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
             ring_pos[0] += 1
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return v, q, ev, (slot_v, slot_q)
+        return v, q, ev, (slot_v, slot_q), n_source
 
     def check(slot):
         nonlocal last_loss
@@ -107,6 +124,8 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
             loss_ev[slot].synchronize()
             last_loss = float(pin_loss[slot][0])
             loss_ev[slot] = None
+            if eng.nvls is not None:
+                eng.nvls.raise_if(int(pin_err[slot][0]))                       # a peer stalled inside the fused data-parallel step
             if not math.isfinite(last_loss):
                 print("Loss is {}, stopping training".format(last_loss))
                 sys.exit(1)
@@ -116,7 +135,7 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
     staged = fetch(nxt) if nxt is not None else None
     step = 0
     while staged is not None:
-        videos, noise, ev, slots = staged
+        videos, noise, ev, slots, eng.n_source = staged
         nxt = next(it_loader, None)
         it = start_steps + step
         for group in opt.param_groups:                                         # run_stage1.py:326-338
@@ -144,6 +163,8 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
             slot = (step // log_freq) & 1
             check(slot)                                                        # the read issued two log points ago
             pin_loss[slot].copy_(loss, non_blocking=True)                      # D2H of this step's loss (async)
+            if eng.nvls is not None:
+                eng.nvls.poll_error_async(pin_err[slot])
             loss_ev[slot] = torch.cuda.Event()
             loss_ev[slot].record()
         if lr_scheduler is not None:

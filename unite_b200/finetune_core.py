@@ -6,7 +6,7 @@ import torch
 
 from . import ops
 from .arena import ParamArena
-from .vit_core import ViTTrunk
+from .vit_core import DropPathSource, ViTTrunk
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -39,6 +39,8 @@ class FinetuneCore:
         self.pos = model.pos_embed[0].to(dev).contiguous()
         self._pos_full: Dict[int, torch.Tensor] = {}
         self._shadow_version = None
+        import os
+        self.drop_path = DropPathSource(model.drop_path_rates, dev, seed=int(os.environ.get("UB_DROP_PATH_SEED", "0")))
 
     def sync_shadow(self, force=False):
         v = self.arena.params_version()

@@ -17,7 +17,7 @@ from . import ops
 from .arena import ParamArena
 from .modeling_finetune import Block, PatchEmbed, _ParamsOnly, drop_path_factors, get_sinusoid_encoding_table
 from .registry import register_model
-from .vit_core import ViTTrunk
+from .vit_core import DropPathSource, ViTTrunk
 
 BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
 
@@ -164,7 +164,7 @@ class AdaptationVisionTransformer(nn.Module):
             vis_idx = (~mask).nonzero()[:, 1].reshape(B, -1).to(I32)   # host sync, as in the reference's x[~mask]
         dp = drop_path_factors_
         if dp is None and self.training:
-            dp = drop_path_factors(self.encoder.drop_path_rates, x.shape[0], x.device)
+            dp = core.drop_path.draw(x.shape[0])
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if need_grad:
             anchor = torch.empty(0, device=x.device, requires_grad=True)
@@ -211,6 +211,8 @@ class AdaptationCore:
         self.clip_pos = model.clip_pos_embed[0].to(dev).contiguous()
         self._shadow_version = None
         self._dec_ws: Dict = {}
+        import os
+        self.drop_path = DropPathSource(enc.drop_path_rates, dev, seed=int(os.environ.get("UB_DROP_PATH_SEED", "0")))
 
     # bf16 shadow of the weights: refreshed whenever a parameter changed outside the fused optimizer
     def sync_shadow(self, force=False):
@@ -234,11 +236,13 @@ class AdaptationCore:
             self._dec_ws[key] = d
         return self._dec_ws[key]
 
-    def run_forward(self, x, vis_idx, patches, dp, clip_only, save, targets=None, loss_acc=None, want_clip=True, abs_rows=None):
+    def run_forward(self, x, vis_idx, patches, dp, clip_only, save, targets=None, loss_acc=None, want_clip=True, abs_rows=None,
+                    loss_clips=None):
         """Returns (x_vis or None, x_clip [K,B,Nv,C] fp32 or None, state).  With `targets` ([K,B,Nv,C] fp32) the decoder
         tail also accumulates the alignment loss mean(2 - 2<out,tgt>) into loss_acc (fp32 [1]).
         want_clip=False skips the alignment decoders (stage 3 only uses the encoder output, run_stage3.py:475-483);
-        abs_rows int32 [B*Nv]: absolute rows of `patches` to gather (committee members share one clip's patches)."""
+        abs_rows int32 [B*Nv]: absolute rows of `patches` to gather (committee members share one clip's patches).
+        loss_clips = (b_lo, b_hi): only these clips enter the loss (clip_loss_data 'source' / 'target', run_stage1.py:418-423)."""
         self.sync_shadow()
         B = x.shape[0]
         Nv = vis_idx.shape[1]
@@ -262,7 +266,8 @@ class AdaptationCore:
         a = self.arena
         enc_w, enc_b = a.p32("encoder.norm.weight"), a.p32("encoder.norm.bias")
         tap_of = {l: k for k, l in enumerate(self.taps)}
-        loss_scale = 1.0 / (K * M)
+        loss_rows = None if loss_clips is None else (loss_clips[0] * Nv, loss_clips[1] * Nv)
+        loss_scale = 1.0 / (K * (M if loss_rows is None else max(1, loss_rows[1] - loss_rows[0])))
 
         def after_layer(l, x_l):
             if l not in tap_of or not want_clip:
@@ -273,7 +278,7 @@ class AdaptationCore:
             ops.layernorm_fwd(x_l, enc_w, enc_b, self.eps, z, post_add=self.clip_pos, post_idx=vis_flat)
             ops.gemm(z, a.b16(f"clip_decoder.{k}.head.weight"), y, bias=a.p32(f"clip_decoder.{k}.head.bias"))
             ops.dec_tail_fwd(y, a.p32(f"clip_decoder.{k}.norm.weight"), a.p32(f"clip_decoder.{k}.norm.bias"), self.eps, out[k],
-                             None if targets is None else targets[k].reshape(M, self.C), loss_acc, loss_scale)
+                             None if targets is None else targets[k].reshape(M, self.C), loss_acc, loss_scale, loss_rows)
 
         ws = self.trunk.forward(p_vis, pos_vis, B, Nv, n_layers, save, dp, after_layer=after_layer)
         x_vis = None
@@ -281,7 +286,7 @@ class AdaptationCore:
             x_vis = torch.empty(M, self.D, device=dev, dtype=F32)
             ops.layernorm_fwd(ws.x_at(self.depth), enc_w, enc_b, self.eps, x_vis)
             x_vis = x_vis.view(B, Nv, self.D)
-        state = dict(ws=ws, dws=dws, B=B, Nv=Nv, M=M, vis_flat=vis_flat, clip_only=clip_only) if save else None
+        state = dict(ws=ws, dws=dws, B=B, Nv=Nv, M=M, vis_flat=vis_flat, clip_only=clip_only, loss_rows=loss_rows) if save else None
         return x_vis, (out.view(K, B, Nv, self.C) if want_clip else None), state
 
     def block_grad_hi(self, l):
@@ -302,10 +307,12 @@ class AdaptationCore:
             go = (targets if targets is not None else g_clip).reshape(K, M, self.C)
             if not go.is_contiguous() or go.dtype != F32:
                 go = go.contiguous().float()
-            go_scale = -2.0 / (K * M) if targets is not None else 1.0
+            go_rows = state.get("loss_rows") if targets is not None else None
+            go_scale = -2.0 / (K * (M if go_rows is None else max(1, go_rows[1] - go_rows[0]))) if targets is not None else 1.0
             for k in range(K):
                 ops.dec_tail_bwd(dws["y"][k], a.p32(f"clip_decoder.{k}.norm.weight"), a.p32(f"clip_decoder.{k}.norm.bias"), self.eps,
-                                 go[k], go_scale, dws["dy"], a.g32(f"clip_decoder.{k}.norm.weight"), a.g32(f"clip_decoder.{k}.norm.bias"))
+                                 go[k], go_scale, dws["dy"], a.g32(f"clip_decoder.{k}.norm.weight"), a.g32(f"clip_decoder.{k}.norm.bias"),
+                                 go_rows)
                 self.trunk._wgrad(dws["dy"], dws["z"][k], a.g32(f"clip_decoder.{k}.head.weight"))
                 ops.colsum_bf16(dws["dy"], a.g32(f"clip_decoder.{k}.head.bias"))
                 ops.gemm(dws["dy"], a.b16(f"clip_decoder.{k}.head.weight"), dws["dz"][k], b_t=True)

@@ -182,7 +182,7 @@ class VisionTransformer(nn.Module):
         core = self.core()
         dp = drop_path_factors_
         if dp is None and self.training:
-            dp = drop_path_factors(self.drop_path_rates, x.shape[0], x.device)
+            dp = core.drop_path.draw(x.shape[0])
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             anchor = torch.empty(0, device=x.device, requires_grad=True)
             return _FinetuneFn.apply(anchor, core, x, dp)

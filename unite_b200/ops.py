@@ -180,16 +180,19 @@ def layernorm_bwd(dy, x, gamma, eps, dx_in, dx_out, dxs_out, row_scale, rows_per
 
 
 @_instrument("dec_tail_fwd", 1)
-def dec_tail_fwd(y, gamma, beta, eps, out, tgt=None, loss_acc=None, loss_scale=0.0):
+def dec_tail_fwd(y, gamma, beta, eps, out, tgt=None, loss_acc=None, loss_scale=0.0, loss_rows=None):
+    """loss_rows = (lo, hi): only these rows enter the loss (clip_loss_data 'source' / 'target'); None = all."""
     rows, D = y.shape
+    lo, hi = loss_rows if loss_rows is not None else (0, rows)
     check(lib.ub_dec_tail_fwd(_p(y, F32, "y"), _p(gamma, F32, "gamma"), _p(beta, F32, "beta"), eps, _p(out, F32, "out"),
-                              _p(tgt, F32, "tgt"), _p(loss_acc, F32, "loss_acc"), loss_scale, rows, D, _stream()), "ub_dec_tail_fwd")
+                              _p(tgt, F32, "tgt"), _p(loss_acc, F32, "loss_acc"), loss_scale, lo, hi, rows, D, _stream()), "ub_dec_tail_fwd")
 
 
 @_instrument("dec_tail_bwd", 1)
-def dec_tail_bwd(y, gamma, beta, eps, go, go_scale, dy_out, dgamma, dbeta):
+def dec_tail_bwd(y, gamma, beta, eps, go, go_scale, dy_out, dgamma, dbeta, go_rows=None):
     rows, D = y.shape
-    check(lib.ub_dec_tail_bwd(_p(y, F32, "y"), _p(gamma, F32, "gamma"), _p(beta, F32, "beta"), eps, _p(go, F32, "go"), go_scale,
+    lo, hi = go_rows if go_rows is not None else (0, rows)
+    check(lib.ub_dec_tail_bwd(_p(y, F32, "y"), _p(gamma, F32, "gamma"), _p(beta, F32, "beta"), eps, _p(go, F32, "go"), go_scale, lo, hi,
                               _p(dy_out, BF16, "dy_out"), _p(dgamma, F32, "dgamma"), _p(dbeta, F32, "dbeta"), rows, D, _stream()),
           "ub_dec_tail_bwd")
 
@@ -269,6 +272,33 @@ def adamw(p, g, m, v, w16, n_decay, lr, wd, beta1, beta2, eps, step, grad_scale=
 def adamw_dev(p, g, m, v, w16, n_decay, hyper, gnorm_sq=None):
     check(lib.ub_adamw_dev(_p(p, F32, "p"), _p(g, F32, "g"), _p(m, F32, "m"), _p(v, F32, "v"), _p(w16, BF16, "w16"), p.numel(), n_decay,
                            _p(hyper, F32, "hyper"), _p(gnorm_sq, F32, "gnorm_sq"), _stream()), "ub_adamw_dev")
+
+
+@_instrument("adamw", 1)
+def adamw_seg(p, g, m, v, w16, seg_end4, hyper, gnorm_sq=None):
+    """Segmented AdamW: seg_end4 int32 [S] (device), hyper fp32 [8 + 2S] (device) — see include/unite_b200.h."""
+    S = seg_end4.numel()
+    if hyper.numel() != 8 + 2 * S:
+        raise _cabi.UBError(f"adamw_seg: hyper has {hyper.numel()} floats, expected {8 + 2 * S}")
+    check(lib.ub_adamw_seg(_p(p, F32, "p"), _p(g, F32, "g"), _p(m, F32, "m"), _p(v, F32, "v"), _p(w16, BF16, "w16"), p.numel(),
+                           _p(seg_end4, I32, "seg_end4"), S, _p(hyper, F32, "hyper"), _p(gnorm_sq, F32, "gnorm_sq"), _stream()), "ub_adamw_seg")
+
+
+@_instrument("sumsq", 1)
+def sumsq_seg(g, seg_end4, hyper, out):
+    check(lib.ub_sumsq_seg(_p(g, F32, "g"), g.numel(), _p(seg_end4, I32, "seg_end4"), seg_end4.numel(), _p(hyper, F32, "hyper"),
+                           _p(out, F32, "out"), _stream()), "ub_sumsq_seg")
+
+
+@_instrument("drop_path_draw", 1)
+def drop_path_draw(rates, out, seed, step):
+    """out fp32 [depth, 2, B] <- DropPath factors of one step; `step` int64 [1] device counter, advanced by the kernel."""
+    depth, two, B = out.shape
+    if two != 2 or rates.numel() != depth or step.dtype != torch.int64 or step.numel() != 1:
+        raise _cabi.UBError("drop_path_draw: out [depth,2,B], rates [depth], step int64 [1] expected")
+    check(lib.ub_drop_path_draw(_p(rates, F32, "rates"), _p(out, F32, "out"), depth, B, int(seed) & 0xFFFFFFFFFFFFFFFF, _p(step, torch.int64, "step"),
+                                _stream()), "ub_drop_path_draw")
+    return out
 
 
 @_instrument("adamw_nvls", 1)

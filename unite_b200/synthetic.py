@@ -38,3 +38,62 @@ class SyntheticStage1Loader:
     def __iter__(self):
         for i in range(self.steps):
             yield self.batches[i % len(self.batches)]
+
+
+class SyntheticStage2Loader:
+    """(clip, label, index, {}) batches of kinetics_sparse.py:159 (train mode), pinned."""
+
+    def __init__(self, batch_size, num_frames=8, img_size=224, steps=10, seed=0, rank=0, n_distinct=2, num_classes=12, pin=True):
+        g = torch.Generator().manual_seed(seed + rank)
+        pin = pin and torch.cuda.is_available()
+        self.steps, self.batches = steps, []
+        for _ in range(n_distinct):
+            v = torch.randn(batch_size, 3, num_frames, img_size, img_size, generator=g)
+            y = torch.randint(0, num_classes, (batch_size,), generator=g)
+            self.batches.append((v.pin_memory() if pin else v, y, torch.arange(batch_size), {}))
+
+    def __len__(self):
+        return self.steps
+
+    def __iter__(self):
+        for i in range(self.steps):
+            yield self.batches[i % len(self.batches)]
+
+
+class SyntheticStage3Loader:
+    """Stage-3 loaders: `.source` yields (clip, label, index, {}) (kinetics_sparse.py:159, train mode) and `.target` yields the
+    dual-view batch (vid, vid_aug, label, name) of validation mode with return_aug_for_val (kinetics_sparse.py:174-180) — the
+    plain view feeds the full-token pass and the zero-shot head, the augmented one the teacher attention and the masked
+    committee (run_stage3.py:405-413).  vid_aug = vid + small noise (a stand-in for RandAugment: a different tensor of the same
+    distribution)."""
+
+    class _Iter:
+        def __init__(self, batches, steps):
+            self.batches, self.steps = batches, steps
+
+        def __len__(self):
+            return self.steps
+
+        def __iter__(self):
+            for i in range(self.steps):
+                yield self.batches[i % len(self.batches)]
+
+    def __init__(self, batch_size_s, batch_size_t=None, num_frames=8, img_size=224, steps=10, seed=0, rank=0, n_distinct=2,
+                 num_classes=12, pin=True):
+        g = torch.Generator().manual_seed(seed + rank)
+        bt = batch_size_t or batch_size_s
+        pin = pin and torch.cuda.is_available()
+        src, tgt = [], []
+        for i in range(n_distinct):
+            vs = torch.randn(batch_size_s, 3, num_frames, img_size, img_size, generator=g)
+            ys = torch.randint(0, num_classes, (batch_size_s,), generator=g)
+            vt = torch.randn(bt, 3, num_frames, img_size, img_size, generator=g)
+            va = vt + 0.1 * torch.randn(bt, 3, num_frames, img_size, img_size, generator=g)
+            yt = torch.randint(0, num_classes, (bt,), generator=g)
+            if pin:
+                vs, vt, va = vs.pin_memory(), vt.pin_memory(), va.pin_memory()
+            src.append((vs, ys, torch.arange(batch_size_s), {}))
+            tgt.append((vt, va, yt, [f"synthetic_{i}_{j}" for j in range(bt)]))
+        self.source = self._Iter(src, steps)
+        self.target = self._Iter(tgt, steps)
+        self.num_classes = num_classes

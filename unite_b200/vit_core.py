@@ -45,6 +45,31 @@ def _splits_for(out_rows: int, out_cols: int, sms: int) -> int:
     return max(1, min(32, sms // max(1, tiles)))
 
 
+class DropPathSource:
+    """Per-step DropPath factors [depth, 2, B] from the device generator (ops.drop_path_draw): one launch per step, no host
+    random numbers, replayable in a CUDA graph.  `step` (device int64) counts the draws made; oracle/philox.py reproduces the
+    factors of any (seed, step) on the host."""
+
+    def __init__(self, rates, device, seed=0):
+        self.rates = [float(r) for r in rates]
+        self.active = any(r > 0 for r in self.rates)
+        self.seed = seed
+        self.device = device
+        if self.active:
+            self.rates_dev = torch.tensor(self.rates, dtype=F32, device=device)
+            self.step = torch.zeros(1, dtype=torch.int64, device=device)
+        self._out = {}
+
+    def draw(self, B, slot=0):
+        """`slot` distinguishes buffers that must stay alive together (several forwards before one backward, stage 3)."""
+        if not self.active:
+            return None
+        key = (B, slot)
+        if key not in self._out:
+            self._out[key] = torch.empty(len(self.rates), 2, B, dtype=F32, device=self.device)
+        return ops.drop_path_draw(self.rates_dev, self._out[key], self.seed, self.step)
+
+
 class _LayerBufs:
     __slots__ = ("h1", "qkv", "o", "lse", "x_mid", "h2", "pre", "act")
 
