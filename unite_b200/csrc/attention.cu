@@ -560,6 +560,18 @@ int launch_attn_fwd_tc(const void* qkv, void* o, int n_seq, int S, int H, float 
 int launch_attn_fwd_lse_tc(const void* qkv, void* o, float* lse, int n_seq, int S, int H, float scale, cudaStream_t stream);
 int launch_attn_bwd_tc(const void* qkv, const void* d_o, const float* lse, const float* Dv, void* dqkv, int n_seq, int S, int H,
                        float scale, cudaStream_t stream);
+int launch_attn_fwd_long_tc(const void* qkv, void* o, float* lse, int n_seq, int S, int H, float scale, cudaStream_t stream);
+int launch_attn_bwd_long_tc(const void* qkv, const void* d_o, const float* lse, const float* Dv, void* dqkv, int n_seq, int S, int H,
+                            float scale, cudaStream_t stream);
+// UB_ATTN_LONG_TC=0: fall back to the mma.sync kernels below for S beyond the short-sequence tcgen05 kernels (debugging only)
+static bool use_long_tc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UB_ATTN_LONG_TC");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
 }
 using namespace ub;
 
@@ -582,6 +594,8 @@ extern "C" int ub_attn_fwd(const void* qkv, void* o, float* lse, int n_seq, int 
     use_tc_lse = e ? atoi(e) : 1;
   }
   if (use_tc_lse && lse != nullptr && S <= 320) return launch_attn_fwd_lse_tc(qkv, o, lse, n_seq, S, H, scale, (cudaStream_t)stream);
+  // everything longer (stage-2 / stage-3 all-token passes, S = 1568): streamed-KV tcgen05 kernel, with or without LSE
+  if (use_long_tc()) return launch_attn_fwd_long_tc(qkv, o, lse, n_seq, S, H, scale, (cudaStream_t)stream);
   dim3 grid((S + TQ - 1) / TQ, H, n_seq);
   UB_LAUNCH(attn_fwd_kernel, grid, 128, 0, (cudaStream_t)stream, (const bf16*)qkv, (bf16*)o, lse, S, H, scale);
   return check_launch("attn_fwd_kernel");
@@ -603,6 +617,7 @@ extern "C" int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, cons
     use_tc = e ? atoi(e) : 1;
   }
   if (use_tc && S <= 320) return launch_attn_bwd_tc(qkv, d_o, lse, D_ws, dqkv, n_seq, S, H, scale, st);
+  if (use_long_tc()) return launch_attn_bwd_long_tc(qkv, d_o, lse, D_ws, dqkv, n_seq, S, H, scale, st);
   dim3 grid((S + TQ - 1) / TQ, H, n_seq);
   constexpr int SMEM_DKV = 6 * TQ * 128 + 4 * TQ * 4;
   constexpr int SMEM_DQ = 6 * TQ * 128;
