@@ -397,3 +397,38 @@ def test_stage3_dual_view_at_256_clips_meets_the_loss_gate_and_trains_through_tr
     assert set(stats) >= {"loss", "loss_class", "loss_class_t", "lr", "min_lr", "weight_decay", "grad_norm"}
     assert all(np.isfinite(stats[k]) for k in ("loss", "loss_class", "loss_class_t", "grad_norm"))
     assert abs(stats["loss"] - (stats["loss_class"] + stats["loss_class_t"])) < 1e-5
+
+
+# ---- stage 2 at full size: all 1568 tokens through the long-sequence tcgen05 attention ---------------------------------------
+def test_full_vitb16_stage2_all_tokens_against_oracle():
+    """BASELINE configs[0] shape on the GPU: ViT-B/16, 8x224^2, every one of the 1568 tokens (S = 1568 attention runs on
+    csrc/attention_long_tc.cu: forward with LSE + two-pass backward), B = 2, against the oracle on the CPU."""
+    from oracle import unite_oracle as O
+    from oracle.weights import seeded_state
+    from unite_b200.engine_for_finetuning import finetune_step
+    scfg = O.StudentCfg(num_classes=12)
+    vit = _build_vit(scfg)
+    vsd = seeded_state({k: tuple(v.shape) for k, v in vit.state_dict().items()}, 3)
+    g = torch.Generator().manual_seed(41)
+    vsd["head.weight"] = torch.randn(vsd["head.weight"].shape, generator=g) * 0.5          # O(1) logits
+    vit.load_state_dict(vsd, strict=True)
+    vit = vit.cuda().eval()
+    videos = torch.randn(2, 3, 8, 224, 224, generator=g)
+    labels = torch.randint(0, 12, (2,), generator=g)
+    ref = O.stage2_step(vsd, videos, labels, scfg)
+    loss = torch.zeros(1, device="cuda")
+    logits = finetune_step(vit, videos.cuda(), labels.cuda(), loss)
+    torch.cuda.synchronize()
+    l_rel = abs(loss.item() - ref["loss"].item()) / ref["loss"].item()
+    print(f"stage-2 full size: logits rel {rel_l2(logits, ref['logits']):.2e}, loss {loss.item():.5f} vs {ref['loss'].item():.5f} ({l_rel:.1e})")
+    assert rel_l2(logits, ref["logits"]) < FEAT_TOL
+    assert l_rel < 5e-3            # a 2-sample CE: its budget is the logit tolerance; the 1e-3 gate is checked at 256 clips above
+    arena = vit.core().arena
+    worst_c, worst_r = 1.0, 0.0
+    for k, g_ref in ref["grads"].items():
+        if g_ref.numel() < 4096:
+            continue
+        c, r = cosine(arena.g32(k), g_ref), rel_l2(arena.g32(k), g_ref)
+        worst_c, worst_r = min(worst_c, c), max(worst_r, r)
+        assert c >= 0.999 and r <= 2e-2, (k, c, r)
+    print(f"stage-2 full size grads: worst cosine {worst_c:.6f}, worst rel-L2 {worst_r:.2e}")
