@@ -7,17 +7,21 @@
 //
 // One kernel template, three modes.  A work unit is a PAIR of 128-row "stationary" tiles of one (sequence, head); warpgroup g owns
 // tile 2*pair+g, and both warpgroups consume the same ring of "streamed" chunks, so every chunk is fetched once per pair:
-//   FWD   stationary Q tile            streamed (K, V) chunks of 128 keys     S = Q K^T -> online softmax -> O += P V, l += P 1
-//   DQ    stationary (Q, dO) tile      streamed (K, V) chunks of 64 keys      S = Q K^T, dP = dO V^T, dS = P o (dP - D) -> dQ += dS K
-//   DKV   stationary (K, V) tile       streamed (Q, dO) chunks of 64 queries  S^T = K Q^T, dP^T = V dO^T -> dV += P^T dO, dK += dS^T Q
+//   FWD   stationary Q tile            streamed (K, V) chunks of 64 keys      S = Q K^T -> online softmax -> O += P V, l += P 1
+//   DQ    stationary (Q, dO) tile      streamed (K, V) chunks of 32 keys      S = Q K^T, dP = dO V^T, dS = P o (dP - D) -> dQ += dS K
+//   DKV   stationary (K, V) tile       streamed (Q, dO) chunks of 32 queries  S^T = K Q^T, dP^T = V dO^T -> dV += P^T dO, dK += dS^T Q
+// Every warpgroup has TWO score sets in TMEM: the scores of chunk n+1 are computed while chunk n is in the softmax threads, so a
+// warpgroup's cycle is load + exponentials + store only.  The stationary tiles are double-buffered too (the next unit's tiles
+// land during the current unit), so units follow each other without a refill bubble.
 // P / dS are written back to TMEM as bf16 over the scores and feed the second product as its A operand (tcgen05.mma TS form);
 // accumulators stay in TMEM for the whole unit, so nothing but the streamed chunks moves during the inner loop.  The backward
 // runs as two passes (DKV then DQ), each with a single writer per output element — a one-pass scheme would have to reduce dQ (or
 // dK / dV) across CTAs with fp32 atomics, ~5 MB per (sequence, head) at S = 1568, which costs more than recomputing S and dP.
 //   warp 0      TMA producer (stationary tiles, streamed ring)          warp 3   DKV: per-chunk log-sum-exp / D loader
 //   warps 1, 2  tcgen05.mma issue streams of warpgroup 0 / 1            warps 4-7 / 8-11   softmax / gradient warpgroups 0 / 1
-// TMEM (256 columns per warpgroup):  FWD  S|P [0,128) O [128,192) l [192,208)     DQ  S [0,64) dP|dS [64,128) dQ [128,192)
-//                                    DKV  S^T|P^T [0,64) dP^T|dS^T [64,128) dV [128,192) dK [192,256)
+// TMEM (256 columns per warpgroup): two score sets at [0,64) and [64,128) — FWD: S|P (64 keys); DQ / DKV: S [0,32) | dP [32,64) with
+//                                    P / dS written over their first 16 columns — then the accumulators: FWD O [128,192) l [192,208);
+//                                    DQ dQ [128,192); DKV dV [128,192) dK [192,256).
 // FWD softmax reference: the row maximum of the first chunk, moved only when a later chunk exceeds it by more than 2^40 (O and l
 // are then rescaled in TMEM) — O / l is invariant under the common factor, so the result is exact and O is normally never touched.
 #include "common.cuh"
@@ -34,17 +38,20 @@ enum { AL_FWD = 0, AL_DQ = 1, AL_DKV = 2 };
 
 template <int MODE>
 struct ALC {
-  static constexpr int NC = MODE == AL_FWD ? 128 : 64;        // streamed rows per chunk
-  static constexpr int NSTG = MODE == AL_FWD ? 3 : 5;         // ring depth
+  static constexpr int NC = MODE == AL_FWD ? 64 : 32;         // streamed rows per chunk
+  static constexpr int NSTG = MODE == AL_FWD ? 5 : 6;         // ring depth
   static constexpr int STAGE_BYTES = 2 * NC * 128;            // two operands of [NC rows][64 bf16]
-  static constexpr int STAT = 0;                               // [2 warpgroups][2 operands][128 rows][64 bf16]
-  static constexpr int RING = 65536;
+  static constexpr int STAT_OPS = MODE == AL_FWD ? 1 : 2;     // stationary operands per warpgroup
+  static constexpr int STAT_WG = STAT_OPS * 16384;            // one stationary tile set
+  static constexpr int STAT = 0;                               // [2 buffers][2 warpgroups][STAT_OPS][128 rows][64 bf16]
+  static constexpr int RING = 4 * STAT_WG;
   static constexpr int OUT = RING + NSTG * STAGE_BYTES;        // 8 warps x 4 KB output staging
   static constexpr int ONES = OUT + 32768;                     // [16][64] bf16 ones (FWD row sums)
-  static constexpr int LD = ONES + 2048;                       // [NSTG][L: 64 | D: 64] fp32 (DKV)
-  static constexpr int BAR = LD + NSTG * 512;
-  static constexpr int NBAR = 3 * NSTG + 14;
+  static constexpr int LD = ONES + (MODE == AL_FWD ? 2048 : 0);   // [NSTG][L: NC | D: NC] fp32 (DKV)
+  static constexpr int BAR = LD + (MODE == AL_DKV ? NSTG * 256 : 0);
+  static constexpr int NBAR = 3 * NSTG + 22;
   static constexpr int SMEM = BAR + NBAR * 8 + 16;
+  static_assert(SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 };
 
 struct AttnLongParams {
@@ -68,14 +75,14 @@ attn_long_tc_kernel(const __grid_constant__ CUtensorMap tmStat, const __grid_con
   uint64_t* ring_full = bars;                  // [NSTG]
   uint64_t* ring_empty = bars + NSTG;          // [NSTG] both warpgroups' products of the chunk have completed
   uint64_t* ld_full = bars + 2 * NSTG;         // [NSTG] DKV: log-sum-exp / D of the chunk's queries are in smem
-  uint64_t* stat_full = bars + 3 * NSTG;       // [2] per warpgroup
-  uint64_t* stat_empty = stat_full + 2;        // [2] every MMA of the unit has read the stationary tile
-  uint64_t* s_full = stat_full + 4;            // [2] scores of the chunk are in TMEM
-  uint64_t* p_ready = stat_full + 6;           // [2] P / dS written back (4 warps)
-  uint64_t* acc_full = stat_full + 8;          // [2] accumulators of the unit are final
-  uint64_t* acc_free = stat_full + 10;         // [2] ... and have been read out (4 warps)
-  uint64_t* pv_done = stat_full + 12;          // [2] FWD: products of the chunk completed (slow path only)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_full + 14);
+  uint64_t* stat_full = bars + 3 * NSTG;       // [2 warpgroups][2 buffers]
+  uint64_t* stat_empty = stat_full + 4;        // [2][2] every MMA of the unit has read the stationary tile
+  uint64_t* s_full = stat_full + 8;            // [2 warpgroups][2 score sets] scores of the chunk are in TMEM
+  uint64_t* p_ready = stat_full + 12;          // [2][2] P / dS written back (4 warps)
+  uint64_t* acc_full = stat_full + 16;         // [2] accumulators of the unit are final
+  uint64_t* acc_free = stat_full + 18;         // [2] ... and have been read out (4 warps)
+  uint64_t* pv_done = stat_full + 20;          // [2] FWD: products of the chunk completed (slow path only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_full + 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -92,11 +99,13 @@ attn_long_tc_kernel(const __grid_constant__ CUtensorMap tmStat, const __grid_con
       mbar_init(&ring_empty[i], 2);
       mbar_init(&ld_full[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&stat_full[i], 1);
       mbar_init(&stat_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], 4);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_free[i], 4);
       mbar_init(&pv_done[i], 1);
@@ -129,21 +138,21 @@ attn_long_tc_kernel(const __grid_constant__ CUtensorMap tmStat, const __grid_con
         int ui = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
           const int item = u / p.npair, pair = u % p.npair, seq = item / p.H, h = item % p.H;
-          for (int g = 0; g < 2; ++g) {
+          const int sb = ui & 1;                                     // stationary buffer of this unit (the next unit's tiles
+          for (int g = 0; g < 2; ++g) {                              // land while this one is still being consumed)
             const int t = min(2 * pair + g, p.ntile - 1);          // an odd tile count: warpgroup 1 repeats the last tile (not stored)
-            uint8_t* dst = smem + C::STAT + g * 32768;
-            mbar_wait(&stat_empty[g], (uint32_t)(ui & 1) ^ 1u);
+            uint8_t* dst = smem + C::STAT + (sb * 2 + g) * C::STAT_WG;
+            uint64_t* fb = &stat_full[g * 2 + sb];
+            mbar_wait(&stat_empty[g * 2 + sb], (uint32_t)((ui >> 1) & 1) ^ 1u);
+            mbar_expect_tx(fb, C::STAT_WG);
             if (MODE == AL_FWD) {
-              mbar_expect_tx(&stat_full[g], 16384);
-              tma_load_3d(&tmStat, &stat_full[g], dst, h * 64, t * 128, seq);
+              tma_load_3d(&tmStat, fb, dst, h * 64, t * 128, seq);
             } else if (MODE == AL_DQ) {
-              mbar_expect_tx(&stat_full[g], 32768);
-              tma_load_3d(&tmStat, &stat_full[g], dst, h * 64, t * 128, seq);
-              tma_load_3d(&tmStatDO, &stat_full[g], dst + 16384, h * 64, t * 128, seq);
+              tma_load_3d(&tmStat, fb, dst, h * 64, t * 128, seq);
+              tma_load_3d(&tmStatDO, fb, dst + 16384, h * 64, t * 128, seq);
             } else {
-              mbar_expect_tx(&stat_full[g], 32768);
-              tma_load_3d(&tmStat, &stat_full[g], dst, (p.H + h) * 64, t * 128, seq);
-              tma_load_3d(&tmStat, &stat_full[g], dst + 16384, (2 * p.H + h) * 64, t * 128, seq);
+              tma_load_3d(&tmStat, fb, dst, (p.H + h) * 64, t * 128, seq);
+              tma_load_3d(&tmStat, fb, dst + 16384, (2 * p.H + h) * 64, t * 128, seq);
             }
           }
           for (int c = 0; c < nchunk; ++c, ++ci) {
@@ -170,54 +179,68 @@ attn_long_tc_kernel(const __grid_constant__ CUtensorMap tmStat, const __grid_con
       constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);
       constexpr uint32_t LO_K = 1u << 16, LO_MN = (8192u >> 4) << 16;
       const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0) + g * 256u;
-      const uint32_t aS0 = ((smem_u32(smem + C::STAT) & 0x3FFFFu) >> 4) + g * 2048u, aS1 = aS0 + 1024u;
+      const uint32_t aStat = (smem_u32(smem + C::STAT) & 0x3FFFFu) >> 4;
       const uint32_t aRing = (smem_u32(smem + C::RING) & 0x3FFFFu) >> 4, aOnes = (smem_u32(smem + C::ONES) & 0x3FFFFu) >> 4;
-      uint32_t ci = 0;
+      uint32_t ci = 0;                         // chunks consumed by this warpgroup; chunk n uses score set n & 1
+      uint32_t si = 0;                         // score MMAs issued (runs up to two chunks ahead of ci)
       int ui = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
-        mbar_wait(&stat_full[g], (uint32_t)(ui & 1));
-        for (int c = 0; c < nchunk; ++c, ++ci) {
-          const uint32_t stage = ci % NSTG;
+        const uint32_t sb = (uint32_t)(ui & 1);
+        const uint32_t aS0 = aStat + (sb * 2u + g) * (uint32_t)(C::STAT_WG >> 4), aS1 = aS0 + 1024u;
+        mbar_wait(&stat_full[g * 2 + sb], (uint32_t)((ui >> 1) & 1));
+        // scores of the next chunk into set (si & 1): S = stat0 x strm0^T (and dP = stat1 x strm1^T)
+        auto issue_scores = [&]() {
+          const uint32_t stage = si % NSTG, set = si & 1u;
           const uint32_t a0 = aRing + stage * (uint32_t)(C::STAGE_BYTES >> 4), a1 = a0 + (uint32_t)((NC * 128) >> 4);
-          mbar_wait(&ring_full[stage], (ci / NSTG) & 1u);
+          mbar_wait(&ring_full[stage], (si / NSTG) & 1u);
           tc_fence_after();
           if (elect_one()) {
+            const uint32_t d = tb + set * 64u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss_lo(tb, aS0 + LO_K + k * 2, HI, a0 + LO_K + k * 2, HI, IDESC_S, k > 0);
+            for (int k = 0; k < 4; ++k) umma_ss_lo(d, aS0 + LO_K + k * 2, HI, a0 + LO_K + k * 2, HI, IDESC_S, k > 0);
             if (MODE != AL_FWD) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_ss_lo(tb + 64, aS1 + LO_K + k * 2, HI, a1 + LO_K + k * 2, HI, IDESC_S, k > 0);
+              for (int k = 0; k < 4; ++k) umma_ss_lo(d + 32, aS1 + LO_K + k * 2, HI, a1 + LO_K + k * 2, HI, IDESC_S, k > 0);
             }
-            umma_commit(&s_full[g]);
+            umma_commit(&s_full[g * 2 + set]);
           }
           __syncwarp();
-          mbar_wait(&p_ready[g], ci & 1u);
+          ++si;
+        };
+        issue_scores();
+        if (nchunk > 1) issue_scores();
+        for (int c = 0; c < nchunk; ++c, ++ci) {
+          const uint32_t stage = ci % NSTG, set = ci & 1u;
+          const uint32_t a0 = aRing + stage * (uint32_t)(C::STAGE_BYTES >> 4), a1 = a0 + (uint32_t)((NC * 128) >> 4);
+          mbar_wait(&p_ready[g * 2 + set], (ci >> 1) & 1u);
           if (c == 0) mbar_wait(&acc_free[g], (uint32_t)(ui & 1) ^ 1u);      // the previous unit's accumulators have been read out
           tc_fence_after();
           if (elect_one()) {
             const bool acc = c > 0;
+            const uint32_t tS = tb + set * 64u;
             if (MODE == AL_FWD) {
 #pragma unroll
-              for (int k = 0; k < NC / 16; ++k) umma_ts_lo(tb + 128, tb + k * 8, a1 + LO_MN + k * 128, HI, IDESC_T, acc || k > 0);
+              for (int k = 0; k < NC / 16; ++k) umma_ts_lo(tb + 128, tS + k * 8, a1 + LO_MN + k * 128, HI, IDESC_T, acc || k > 0);
 #pragma unroll
-              for (int k = 0; k < NC / 16; ++k) umma_ts_lo(tb + 192, tb + k * 8, aOnes + LO_K, HI, IDESC_R, acc || k > 0);
+              for (int k = 0; k < NC / 16; ++k) umma_ts_lo(tb + 192, tS + k * 8, aOnes + LO_K, HI, IDESC_R, acc || k > 0);
               umma_commit(&pv_done[g]);
             } else if (MODE == AL_DQ) {
 #pragma unroll
-              for (int k = 0; k < NC / 16; ++k) umma_ts_lo(tb + 128, tb + 64 + k * 8, a0 + LO_MN + k * 128, HI, IDESC_T, acc || k > 0);
+              for (int k = 0; k < NC / 16; ++k) umma_ts_lo(tb + 128, tS + 32 + k * 8, a0 + LO_MN + k * 128, HI, IDESC_T, acc || k > 0);
             } else {
 #pragma unroll
-              for (int k = 0; k < NC / 16; ++k) umma_ts_lo(tb + 128, tb + k * 8, a1 + LO_MN + k * 128, HI, IDESC_T, acc || k > 0);
+              for (int k = 0; k < NC / 16; ++k) umma_ts_lo(tb + 128, tS + k * 8, a1 + LO_MN + k * 128, HI, IDESC_T, acc || k > 0);
 #pragma unroll
-              for (int k = 0; k < NC / 16; ++k) umma_ts_lo(tb + 192, tb + 64 + k * 8, a0 + LO_MN + k * 128, HI, IDESC_T, acc || k > 0);
+              for (int k = 0; k < NC / 16; ++k) umma_ts_lo(tb + 192, tS + 32 + k * 8, a0 + LO_MN + k * 128, HI, IDESC_T, acc || k > 0);
             }
             umma_commit(&ring_empty[stage]);
             if (c == nchunk - 1) {
               umma_commit(&acc_full[g]);
-              umma_commit(&stat_empty[g]);
+              umma_commit(&stat_empty[g * 2 + sb]);
             }
           }
           __syncwarp();
+          if (c + 2 < nchunk) issue_scores();     // into the set whose P / dS the products above have just consumed (in issue order)
         }
       }
     } else if (MODE == AL_DKV) {
@@ -230,11 +253,11 @@ attn_long_tc_kernel(const __grid_constant__ CUtensorMap tmStat, const __grid_con
         for (int c = 0; c < nchunk; ++c, ++ci) {
           const uint32_t stage = ci % NSTG, ph = (ci / NSTG) & 1u;
           mbar_wait(&ring_empty[stage], ph ^ 1u);
-          float* sL = reinterpret_cast<float*>(smem + C::LD + stage * 512);
-          for (int i = lane; i < 64; i += 32) {
-            const int q = c * 64 + i;
-            sL[i] = q < p.S ? __ldg(gL + q) * 1.4426950408889634f : INFINITY;     // +inf -> P = 0 for padded queries
-            sL[64 + i] = q < p.S ? __ldg(gD + q) : 0.f;
+          float* sL = reinterpret_cast<float*>(smem + C::LD + stage * 256);
+          {
+            const int q = c * NC + lane;                                           // NC == 32: one query per lane
+            sL[lane] = q < p.S ? __ldg(gL + q) * 1.4426950408889634f : INFINITY;   // +inf -> P = 0 for padded queries
+            sL[NC + lane] = q < p.S ? __ldg(gD + q) : 0.f;
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&ld_full[stage]);
@@ -279,6 +302,19 @@ attn_long_tc_kernel(const __grid_constant__ CUtensorMap tmStat, const __grid_con
         tma_store_commit();
       }
     };
+    // The TMEM read port (64 B/clk/SM) bounds every mode (4 B of scores per (query, key) pair forward, 8 B backward), with the
+    // MUFU (16 ex2/clk/SM) right behind it.  -DUB_AL_PINGPONG makes the score loads of the two warpgroups strictly alternate
+    // (named barriers 2 / 3); measured on B200 at S = 1568 it changes nothing (575 vs 584 us forward), so it is off: what
+    // mattered was taking the score MMAs off each warpgroup's critical path (two score sets, issued one chunk ahead).
+    auto my_turn = [&]() {
+      if (g == 0) asm volatile("bar.sync 2, 256;" ::: "memory"); else asm volatile("bar.sync 3, 256;" ::: "memory");
+    };
+    auto pass_turn = [&]() {
+      if (g == 0) asm volatile("bar.arrive 3, 256;" ::: "memory"); else asm volatile("bar.arrive 2, 256;" ::: "memory");
+    };
+#ifdef UB_AL_PINGPONG
+    if (g == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");      // warpgroup A goes first
+#endif
     uint32_t ci = 0;
     int ui = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
@@ -294,15 +330,22 @@ attn_long_tc_kernel(const __grid_constant__ CUtensorMap tmStat, const __grid_con
         dd = __ldg(p.Dv + (int64_t)item * p.S + row);
       }
       for (int c = 0; c < nchunk; ++c, ++ci) {
-        const uint32_t stage = ci % NSTG;
-        mbar_wait(&s_full[g], ci & 1u);
+        const uint32_t stage = ci % NSTG, set = ci & 1u;
+        const uint32_t t_set = t_row + set * 64u;
+        mbar_wait(&s_full[g * 2 + set], (ci >> 1) & 1u);
         tc_fence_after();
         if (MODE == AL_FWD) {
           const int kvalid = min(NC, p.S - c * NC);
           uint32_t sv[NC];
+#ifdef UB_AL_PINGPONG
+          my_turn();
+#endif
 #pragma unroll
-          for (int q = 0; q < NC / 32; ++q) tmem_ld_32x32(t_row + q * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[q * 32]));
+          for (int q = 0; q < NC / 32; ++q) tmem_ld_32x32(t_set + q * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[q * 32]));
           tmem_ld_wait();
+#ifdef UB_AL_PINGPONG
+          pass_turn();
+#endif
           float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
           if (kvalid == NC) {
 #pragma unroll
@@ -355,65 +398,59 @@ attn_long_tc_kernel(const __grid_constant__ CUtensorMap tmStat, const __grid_con
               }
               pk[i] = pack_bf16x2(p0, p1);
             }
-            tmem_st_32x16(t_row + q * 16, pk);
+            tmem_st_32x16(t_set + q * 16, pk);
           }
         } else {
-          uint32_t sv[64], dv[64];
-          tmem_ld_32x32(t_row, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
-          tmem_ld_32x32(t_row + 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[32]));
-          tmem_ld_32x32(t_row + 64, *reinterpret_cast<uint32_t(*)[32]>(&dv[0]));
-          tmem_ld_32x32(t_row + 96, *reinterpret_cast<uint32_t(*)[32]>(&dv[32]));
-          // two halves of 32 columns: P / dS of half hf land on columns whose scores were already read in half 0
+          // set = {S [0,32) | dP [32,64)}; P / dS (bf16, 16 columns each) are written over the first half of S / dP
+          uint32_t sv[32], dv[32];
+          if (MODE == AL_DKV) mbar_wait(&ld_full[stage], (ci / NSTG) & 1u);
+#ifdef UB_AL_PINGPONG
+          my_turn();
+#endif
+          tmem_ld_32x32(t_set, sv);
+          tmem_ld_32x32(t_set + 32, dv);
+          tmem_ld_wait();
+#ifdef UB_AL_PINGPONG
+          pass_turn();
+#endif
+          uint32_t pk[16], dk[16];
           if (MODE == AL_DQ) {
             const int kvalid = min(NC, p.S - c * NC);
-            tmem_ld_wait();
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              uint32_t dk[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int k0 = hf * 32 + 2 * i;
-                const float p0 = fast_exp2(fmaf(__uint_as_float(sv[k0]), sl2, -l2));
-                const float p1 = fast_exp2(fmaf(__uint_as_float(sv[k0 + 1]), sl2, -l2));
-                float d0 = p0 * (__uint_as_float(dv[k0]) - dd), d1 = p1 * (__uint_as_float(dv[k0 + 1]) - dd);
-                if (kvalid != NC) {
-                  if (k0 >= kvalid) d0 = 0.f;
-                  if (k0 + 1 >= kvalid) d1 = 0.f;
-                }
-                dk[i] = pack_bf16x2(d0, d1);
+            for (int i = 0; i < 16; ++i) {
+              const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * i]), sl2, -l2));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -l2));
+              float d0 = p0 * (__uint_as_float(dv[2 * i]) - dd), d1 = p1 * (__uint_as_float(dv[2 * i + 1]) - dd);
+              if (kvalid != NC) {
+                if (2 * i >= kvalid) d0 = 0.f;
+                if (2 * i + 1 >= kvalid) d1 = 0.f;
               }
-              tmem_st_32x16(t_row + 64 + hf * 16, dk);
+              dk[i] = pack_bf16x2(d0, d1);
             }
+            tmem_st_32x16(t_set + 32, dk);
           } else {
-            mbar_wait(&ld_full[stage], (ci / NSTG) & 1u);
-            const float4* L4 = reinterpret_cast<const float4*>(smem + C::LD + stage * 512);
-            const float4* D4 = L4 + 16;
-            tmem_ld_wait();
+            const float4* L4 = reinterpret_cast<const float4*>(smem + C::LD + stage * 256);
+            const float4* D4 = L4 + NC / 4;
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              uint32_t pk[16], dk[16];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int k0 = hf * 32 + 4 * i;
-                const float4 l = L4[hf * 8 + i], d = D4[hf * 8 + i];
-                const float p0 = fast_exp2(fmaf(__uint_as_float(sv[k0]), sl2, -l.x));
-                const float p1 = fast_exp2(fmaf(__uint_as_float(sv[k0 + 1]), sl2, -l.y));
-                const float p2 = fast_exp2(fmaf(__uint_as_float(sv[k0 + 2]), sl2, -l.z));
-                const float p3 = fast_exp2(fmaf(__uint_as_float(sv[k0 + 3]), sl2, -l.w));
-                pk[2 * i] = pack_bf16x2(p0, p1);
-                pk[2 * i + 1] = pack_bf16x2(p2, p3);
-                dk[2 * i] = pack_bf16x2(p0 * (__uint_as_float(dv[k0]) - d.x), p1 * (__uint_as_float(dv[k0 + 1]) - d.y));
-                dk[2 * i + 1] = pack_bf16x2(p2 * (__uint_as_float(dv[k0 + 2]) - d.z), p3 * (__uint_as_float(dv[k0 + 3]) - d.w));
-              }
-              tmem_st_32x16(t_row + hf * 16, pk);
-              tmem_st_32x16(t_row + 64 + hf * 16, dk);
+            for (int i = 0; i < 8; ++i) {
+              const float4 l = L4[i], d = D4[i];
+              const float p0 = fast_exp2(fmaf(__uint_as_float(sv[4 * i]), sl2, -l.x));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(sv[4 * i + 1]), sl2, -l.y));
+              const float p2 = fast_exp2(fmaf(__uint_as_float(sv[4 * i + 2]), sl2, -l.z));
+              const float p3 = fast_exp2(fmaf(__uint_as_float(sv[4 * i + 3]), sl2, -l.w));
+              pk[2 * i] = pack_bf16x2(p0, p1);
+              pk[2 * i + 1] = pack_bf16x2(p2, p3);
+              dk[2 * i] = pack_bf16x2(p0 * (__uint_as_float(dv[4 * i]) - d.x), p1 * (__uint_as_float(dv[4 * i + 1]) - d.y));
+              dk[2 * i + 1] = pack_bf16x2(p2 * (__uint_as_float(dv[4 * i + 2]) - d.z), p3 * (__uint_as_float(dv[4 * i + 3]) - d.w));
             }
+            tmem_st_32x16(t_set, pk);
+            tmem_st_32x16(t_set + 32, dk);
           }
         }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_ready[g]);
+        if (lane == 0) mbar_arrive(&p_ready[g * 2 + set]);
       }
       // ---- accumulators of the unit -> global
       mbar_wait(&acc_full[g], (uint32_t)(ui & 1));
@@ -435,6 +472,9 @@ attn_long_tc_kernel(const __grid_constant__ CUtensorMap tmStat, const __grid_con
       if (lane == 0) mbar_arrive(&acc_free[g]);
     }
     if (lane == 0) tma_store_wait_read<0>();
+#ifdef UB_AL_PINGPONG
+    if (g == 0) my_turn();                      // takes warpgroup B's last hand-over
+#endif
   }
   tc_fence_before();
   __syncthreads();
