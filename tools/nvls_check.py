@@ -82,6 +82,34 @@ def main():
             ok = False
             print(f"[rank {rank}] {name}: max abs diff {float((a - b).abs().max()):.3e}", flush=True)
 
+    # ---- clip_grad with the fused step (NvlsShardedStep.step_dev_clipped) against all-reduce -> clip coefficient -> AdamW ----
+    # both paths continue from the consolidated state above (identical on every rank)
+    ref_a.params.copy_(new_a.params); ref_o.exp_avg.copy_(new_o.exp_avg); ref_o.exp_avg_sq.copy_(new_o.exp_avg_sq)
+    grads = torch.randn(n, device=dev, generator=gr) * 1e-3
+    step = args.steps + 1
+    hyper = torch.tensor([1e-3, 0.05, b1, b2, 1e-8, 1 - b1 ** step, math.sqrt(1 - b2 ** step), 1.0 / world], device=dev)
+    ref_o._hyper_dev.copy_(hyper); new_o._hyper_dev.copy_(hyper)
+    ref_a.grads.copy_(grads)
+    dist.all_reduce(ref_a.grads)
+    total = ref_a.grads.double().norm().item() / world                       # norm of the averaged gradient
+    max_norm = 0.3 * total
+    coef = min(1.0, max_norm / (total + 1e-6))
+    h2 = hyper.clone(); h2[7] = coef / world
+    ops.adamw_dev(ref_a.params, ref_a.grads, ref_o.exp_avg, ref_o.exp_avg_sq, ref_a.w16, n_decay, h2, None)
+    new_a.grads.copy_(grads)
+    nv.step_dev_clipped(max_norm)
+    torch.cuda.synchronize()
+    nv.check()
+    nv.consolidate()
+    torch.cuda.synchronize()
+    gn = new_o.gnorm_sq.sqrt().item() / world
+    if abs(gn - total) > 1e-4 * total:
+        ok = False
+        print(f"[rank {rank}] clipped step: reported grad norm {gn} vs {total}", flush=True)
+    if not torch.allclose(new_a.params, ref_a.params, rtol=1e-5, atol=2e-5):
+        ok = False
+        print(f"[rank {rank}] clipped step: p max abs diff {float((new_a.params - ref_a.params).abs().max()):.3e}", flush=True)
+
     # ---- timing -------------------------------------------------------------------------------------------------
     def timeit(fn):
         for _ in range(3):
