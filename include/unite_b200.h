@@ -206,13 +206,16 @@ UB_API int ub_drop_path_draw(const float* rates, float* out, int depth, int B, u
  * stage_peers (every rank's mapping of a symmetric staging buffer of world * ceil(n_decay/8/world) * 8 floats): selects the
  * PUSH form — each rank first writes its gradients of every peer's slice into slot[rank] of that peer's staging buffer
  * (posted NVLink writes), a grid-wide cross-GPU counter follows, then the owner sums local copies in rank order.
+ * prepushed != 0 (push form only): the caller has ALREADY filled the staging buffers — slot[rank] of every peer holds this rank's
+ * gradients of that peer's slice — with peer-to-peer copies issued during backward and stream-ordered before this launch (the
+ * overlap DistributedDataParallel gets from bucketed all-reduces); the kernel then skips its scatter phase and the mid barrier.
  * ---------------------------------------------------------------------------------------------- */
 UB_API int ub_nvls_slots(void);
 UB_API int ub_adamw_nvls(float* p, const float* g_mc, float* m, float* v, void* w16, void* w16_mc, int64_t n, int64_t n_decay,
                          int rank, int world, const float* hyper, float* gnorm_sq_mc /* may be NULL */, uint32_t* flags,
                          uint32_t* flags_mc, uint32_t* epoch, int32_t* err, const void* const* g_peers /* host array [world] or NULL */,
                          void* const* w16_peers /* host array [world] or NULL */,
-                         void* const* stage_peers /* host array [world] or NULL */, void* stream);
+                         void* const* stage_peers /* host array [world] or NULL */, int prepushed, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Classification heads and stage-3 pseudo-label fusion (fp32, small).

@@ -90,6 +90,7 @@ struct NvlsStep {
   int mc_store;                  // 1: shadow written through the multicast address, 0: one plain store per peer
   float* stage_peer[8];          // push mode: every rank's mapping of the staging buffer [world][shard] (slot s = rank s's gradients)
   uint32_t* mid; uint32_t* mid_mc;   // push mode: grid-wide cross-GPU counter between the scatter and the update phase
+  int prepushed;                     // push mode: the staging buffers were already filled by copy-engine pushes during backward
 };
 
 template <int kW, bool kDecay, bool kBroadcast, bool kNorm>
@@ -257,8 +258,11 @@ __global__ void __launch_bounds__(256) adamw_push_kernel(const NvlsStep a) {
   const long shard = (a.n8_decay + kW - 1) / kW;
   const float4* g_local = reinterpret_cast<const float4*>(a.g_peer[a.rank]);
   // ---- phase A: scatter my gradients to their owners (staggered start so that the N ranks hit N different peers) ----
+  // prepushed: every rank's slices already sit in the owners' staging buffers — peer-to-peer copies on the copy engines, issued
+  // range by range while backward was still running (ddp.NvlsShardedStep.range_ready) and stream-ordered before this launch, so
+  // once the entry barrier has seen every rank's kernel start, every push has landed: no scatter, no mid barrier.
 #pragma unroll 1
-  for (int j = 1; j < kW; ++j) {
+  for (int j = 1; j < (a.prepushed ? 1 : kW); ++j) {
     const int q = (a.rank + j) % kW;
     const long qlo = min((long)q * shard, a.n8_decay), qhi = min(qlo + shard, a.n8_decay);
     const float4* src = g_local + 2 * qlo;
@@ -277,8 +281,8 @@ __global__ void __launch_bounds__(256) adamw_push_kernel(const NvlsStep a) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
-    mc_signal(a.mid_mc);
-    if (!wait_ge(a.mid, (s_epoch + 1u) * (uint32_t)(kW * nb), a.spin_limit, a.err, 3)) s_abort = 1;
+    mc_signal(a.mid_mc);               // always counted (the counter is monotone over launches), only waited for after a scatter
+    if (!a.prepushed && !wait_ge(a.mid, (s_epoch + 1u) * (uint32_t)(kW * nb), a.spin_limit, a.err, 3)) s_abort = 1;
   }
   __syncthreads();
   if (s_abort) return;                   // some rank's gradients never arrived: leave p / m / v and the shadows alone
@@ -349,7 +353,7 @@ extern "C" int ub_nvls_slots(void) { return 2 * sm_count() * kNvlsMaxCtasPerSm +
 extern "C" int ub_adamw_nvls(float* p, const float* g_mc, float* m, float* v, void* w16, void* w16_mc, int64_t n, int64_t n_decay,
                              int rank, int world, const float* hyper, float* gnorm_sq_mc, uint32_t* flags, uint32_t* flags_mc,
                              uint32_t* epoch, int32_t* err, const void* const* g_peers, void* const* w16_peers,
-                             void* const* stage_peers, void* stream) {
+                             void* const* stage_peers, int prepushed, void* stream) {
   UB_REQUIRE(p && g_mc && m && v && w16 && w16_mc && hyper && flags && flags_mc && epoch && err, "adamw_nvls: null pointer");
   UB_REQUIRE(n > 0 && n % 8 == 0 && n_decay % 8 == 0 && n_decay >= 0 && n_decay <= n,
              "adamw_nvls: n=%lld and n_decay=%lld must be multiples of 8", (long long)n, (long long)n_decay);
@@ -379,6 +383,8 @@ extern "C" int ub_adamw_nvls(float* p, const float* g_mc, float* m, float* v, vo
   const bool push = p2p && stage_peers != nullptr && nvls_mode() == 2;
   const int slots_half = sm_count() * kNvlsMaxCtasPerSm;
   for (int r = 0; r < 8; ++r) a.stage_peer[r] = push && r < world ? (float*)stage_peers[r] : nullptr;
+  UB_REQUIRE(!prepushed || push, "adamw_nvls: prepushed needs the push form (stage_peers, world 2 / 4 / 8, UB_NVLS_MODE=push)");
+  a.prepushed = prepushed ? 1 : 0;
   a.mid = flags + 2 * slots_half;                       // one counter right behind the entry / exit slots
   a.mid_mc = flags_mc + 2 * slots_half;
   if (push) {

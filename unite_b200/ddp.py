@@ -121,6 +121,17 @@ class NvlsShardedStep:
         self.stage_peers = (ctypes.c_void_p * self.world)(*[int(a) for a in self._hdl[3].buffer_ptrs])
         self.flags = self._sync.data_ptr() + 32
         self.calls = 0
+        # ---- gradient pushes overlapped with backward (the role of DDP's bucketed all-reduce, run_stage1.py:809): as soon as a
+        # prefix of the decay segment is final, its pieces go to the owners' staging slots as peer-to-peer copies on the copy
+        # engines (no SM is taken from the backward GEMMs); the fused kernel then starts at the reduce + AdamW phase
+        self.early_push = _os.environ.get("UB_NVLS_EARLY_PUSH", "1") != "0" and _os.environ.get("UB_NVLS_MODE", "push") == "push" \
+            and self.world in (2, 4, 8)
+        self._push_stream = torch.cuda.Stream(device=dev) if self.early_push else None
+        self._pushed_hi = 0
+        self._shard = self.shard_of(arena.n_decay, 0, self.world)[1]            # elements per (full) shard
+        self._stage_of = [self._hdl[3].get_buffer(r, (self._stage.numel(),), torch.float32) if r != self.rank else None
+                          for r in range(self.world)] if self.early_push else None
+        self.pushes = 0
         torch.cuda.synchronize(dev)
         dist.barrier(self.pg)                                      # every rank's buffers are initialised before anyone's kernel
         torch.cuda.synchronize(dev)
@@ -137,13 +148,46 @@ class NvlsShardedStep:
     def shard_range(self, rank=None):
         return self.shard_of(self.arena.n_decay, self.rank if rank is None else rank, self.world)
 
+    def range_ready(self, flat: torch.Tensor, hi: int):
+        """GradSync.range_ready's twin for the fused step: the decay-segment prefix [pushed, hi) of the gradient arena is final
+        (backward has finished those blocks) — push its pieces to the ranks that own them, asynchronously, on the copy engines."""
+        if not self.early_push:
+            return
+        hi = min(hi, self.arena.n_decay)
+        if hi <= self._pushed_hi:
+            if hi < self._pushed_hi:
+                self._pushed_hi = 0                   # a new backward without an optimizer step in between: start over
+            else:
+                return
+        lo, self._pushed_hi = self._pushed_hi, hi
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.arena.device))
+        self._push_stream.wait_event(ev)
+        g = self.arena.grads
+        with torch.cuda.stream(self._push_stream):
+            for j in range(1, self.world):
+                q = (self.rank + j) % self.world          # staggered: the N ranks address N different peers at any time
+                qlo, qhi = self.shard_range(q)
+                a, b = max(lo, qlo), min(hi, qhi)
+                if b > a:
+                    off = self.rank * self._shard + (a - qlo)
+                    self._stage_of[q][off:off + (b - a)].copy_(g[a:b], non_blocking=True)
+                    self.pushes += 1
+
     def step_dev(self):
         """Device side of the step (graph-capturable); the optimizer's prepare_step() uploaded hyper[] with grad_scale = 1/world."""
         from . import ops
         a, o = self.arena, self.opt
+        prepushed = False
+        if self.early_push and self._pushed_hi > 0:
+            self.range_ready(a.grads, a.n_decay)          # whatever backward finished last (the patch embedding)
+            torch.cuda.current_stream(a.device).wait_stream(self._push_stream)
+            prepushed = True
+        self._pushed_hi = 0
         o.gnorm_sq.zero_()
         ops.adamw_nvls(a.params, self.g_mc, o.exp_avg, o.exp_avg_sq, a.w16, self.w16_mc, a.n_decay, self.rank, self.world,
-                       o._hyper_dev, self.gnorm_mc, self.flags, self.flags_mc, self._epoch, self._err, self.g_peers, self.w16_peers, self.stage_peers)
+                       o._hyper_dev, self.gnorm_mc, self.flags, self.flags_mc, self._epoch, self._err, self.g_peers, self.w16_peers, self.stage_peers,
+                       prepushed=prepushed)
         self.calls += 1
 
     def step_dev_clipped(self, max_norm: float):
@@ -154,6 +198,9 @@ class NvlsShardedStep:
         Slower than the unclipped step by one all-reduce; clip_grad is null in every shipped config."""
         from . import ops
         a, o = self.arena, self.opt
+        if self._pushed_hi > 0:                           # pushes of unreduced gradients are of no use here: let them finish, ignore them
+            torch.cuda.current_stream(a.device).wait_stream(self._push_stream)
+            self._pushed_hi = 0
         dist.all_reduce(a.grads, op=dist.ReduceOp.SUM, group=self.pg)
         if not hasattr(self, "_clip_sq"):
             self._clip_sq = torch.zeros(1, device=a.device, dtype=torch.float32)

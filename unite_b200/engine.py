@@ -334,7 +334,7 @@ class Stage1Engine:
             # shipped config: the loss and its gradient are fused into the decoder-tail kernels
             _, x_clip, state = core.run_forward(videos, vis_idx[0], patches_s, dp, True, True,
                                                 targets=targets, loss_acc=self.loss, loss_clips=loss_clips)
-            core.run_backward(state, targets=targets, grad_sync=None if self.nvls is not None else self.grad_sync)
+            core.run_backward(state, targets=targets, grad_sync=self._backward_hook())
         else:
             # run_stage1.py:403-408,432-433 (nn.MSELoss / nn.SmoothL1Loss / nn.L1Loss, mean reduction): loss value and
             # d loss / d outputs are a few element-wise device ops on the [K,B,Nv,C] outputs; the rest of backward is shared
@@ -360,9 +360,17 @@ class Stage1Engine:
                 g = d.sign() / n                                                   # sign(0) = 0 on the rows outside the slice
             else:
                 raise NotImplementedError(f"clip_loss_type={kind!r} (run_stage1.py:430-435 raises for anything else too)")
-            core.run_backward(state, g_clip=g, grad_sync=None if self.nvls is not None else self.grad_sync)
+            core.run_backward(state, g_clip=g, grad_sync=self._backward_hook())
         self.last = dict(attn=attn, mask=mask.view(B, Tp * P).bool(), vis_idx=vis_idx[0], targets=targets, outputs=x_clip)
         return self.loss
+
+    def _backward_hook(self):
+        """Who is told, block by block, that a prefix of the gradient arena is final: the fused NVLink step (copy-engine pushes
+        to the owning ranks) or the NCCL path (range all-reduces); both overlap the rest of backward.  With clip_grad the fused
+        step needs the summed gradient first (NvlsShardedStep.step_dev_clipped), so nothing is pushed early."""
+        if self.nvls is not None:
+            return self.nvls if (self.nvls.early_push and not self.max_norm) else None
+        return self.grad_sync
 
     def _loss_clips(self, B):
         """Clip range [lo, hi) of the batch that enters the alignment loss (run_stage1.py:418-423); None = all ('mixed')."""

@@ -303,14 +303,15 @@ def drop_path_draw(rates, out, seed, step):
 
 @_instrument("adamw_nvls", 1)
 def adamw_nvls(p, g_mc, m, v, w16, w16_mc, n_decay, rank, world, hyper, gnorm_mc, flags, flags_mc, epoch, err, g_peers=None,
-               w16_peers=None, stage_peers=None):
+               w16_peers=None, stage_peers=None, prepushed=False):
     """g_mc / w16_mc / gnorm_mc / flags / flags_mc are raw addresses (ints): multicast mappings of symmetric allocations;
     g_peers / w16_peers: ctypes arrays of every rank's mapping of the gradient arena / shadow (or None)."""
     check(lib.ub_adamw_nvls(_p(p, F32, "p"), g_mc, _p(m, F32, "m"), _p(v, F32, "v"), _p(w16, BF16, "w16"), w16_mc, p.numel(), n_decay,
                             rank, world, _p(hyper, F32, "hyper"), gnorm_mc, flags, flags_mc, epoch.data_ptr(), err.data_ptr(),
                             None if g_peers is None else _cabi.C.addressof(g_peers),
                             None if w16_peers is None else _cabi.C.addressof(w16_peers),
-                            None if stage_peers is None else _cabi.C.addressof(stage_peers), _stream()), "ub_adamw_nvls")
+                            None if stage_peers is None else _cabi.C.addressof(stage_peers), int(bool(prepushed)), _stream()),
+          "ub_adamw_nvls")
 
 
 @_instrument("cast_bf16", 1)
