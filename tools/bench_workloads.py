@@ -69,7 +69,7 @@ def run_workload(args, rank, local, world, dev, ClockSampler, measured_peaks, F_
             i[0] += 1
             opt.zero_grad()
             loss.zero_()
-            finetune_step(model, v, y, loss)
+            finetune_step(model, v, y, loss, grad_sync=gs)
             scale = gs.all_reduce(model.core().arena.grads) if gs is not None else 1.0
             opt.step(grad_scale=scale)
             return loss

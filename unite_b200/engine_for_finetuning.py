@@ -34,8 +34,10 @@ def _default_optimizer(net):
     return opt
 
 
-def finetune_step(model, samples, targets, loss_acc, scale=1.0):
-    """One micro-step: forward, CE, backward.  Adds scale * mean CE to loss_acc (fp32 [1]).  Returns logits."""
+def finetune_step(model, samples, targets, loss_acc, scale=1.0, grad_sync=None):
+    """One micro-step: forward, CE, backward.  Adds scale * mean CE to loss_acc (fp32 [1]).  Returns logits.
+    grad_sync: pass the model's GradSync on the micro-step that is followed by the optimizer step — its range all-reduces then
+    overlap this backward."""
     net = model.module if hasattr(model, "module") else model
     core = net.core()
     dp = core.drop_path.draw(samples.shape[0]) if net.training else None       # modeling_finetune.py:42-50 (device-side draws)
@@ -43,7 +45,7 @@ def finetune_step(model, samples, targets, loss_acc, scale=1.0):
     B = logits.shape[0]
     dlogits = torch.empty_like(logits)
     ops.softmax_ce(logits, targets.to(torch.int32), None, scale / B, loss_acc, dlogits)
-    core.run_backward(state, dlogits)
+    core.run_backward(state, dlogits, grad_sync=grad_sync)
     return logits
 
 
@@ -75,6 +77,8 @@ def train_one_epoch(model: torch.nn.Module, criterion=None, data_loader: Iterabl
     for data_iter_step, batch in enumerate(data_loader):
         samples, targets = batch[0], batch[1]
         step = data_iter_step // update_freq
+        if num_training_steps_per_epoch is not None and step >= num_training_steps_per_epoch:
+            continue                                                               # engine_for_finetuning.py:71-72
         it = start_steps + step
         if data_iter_step % update_freq == 0:
             for group in optimizer.param_groups:                                   # engine_for_finetuning.py:76-81
@@ -85,7 +89,8 @@ def train_one_epoch(model: torch.nn.Module, criterion=None, data_loader: Iterabl
         samples = samples.to(dev, non_blocking=True)
         targets = targets.to(dev, non_blocking=True)
         loss_acc.zero_()
-        logits = finetune_step(model, samples, targets, loss_acc, scale=1.0 / update_freq)
+        last_micro = (data_iter_step + 1) % update_freq == 0
+        logits = finetune_step(model, samples, targets, loss_acc, scale=1.0 / update_freq, grad_sync=gs if last_micro else None)
         loss_sum += loss_acc * update_freq
         correct += (logits.argmax(-1) == targets).sum()
         seen += samples.shape[0]

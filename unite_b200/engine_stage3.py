@@ -65,13 +65,13 @@ class Stage3Engine:
         ops.linear_small_fwd(pooled, self.W, self.b, logits)
         return pooled, logits
 
-    def _backward_from_logits(self, state, pooled, dlogits, n_tokens):
+    def _backward_from_logits(self, state, pooled, dlogits, n_tokens, grad_sync=None):
         B, D = pooled.shape
         d_pooled = torch.empty(B, D, device=pooled.device, dtype=F32)
         ops.linear_small_bwd(pooled, self.W, dlogits, d_pooled, None, None)       # classifier frozen: dx only
         g_vis = torch.empty(B, n_tokens, D, device=pooled.device, dtype=F32)
         ops.meanpool_bwd(d_pooled, g_vis)
-        self.core.run_backward(state, g_vis=g_vis, grad_sync=None)
+        self.core.run_backward(state, g_vis=g_vis, grad_sync=grad_sync)
 
     def forward_backward(self, videos_s, labels_s, videos_t, videos_t_aug: Optional[torch.Tensor] = None,
                          attn_override: Optional[torch.Tensor] = None, dp_override=None):
@@ -141,7 +141,8 @@ class Stage3Engine:
         ops.pseudo_label_fusion(logits_full_t, clip_probs, self.thr, self.conf_weighted, msp, pseudo, sel, weight)
         dl_t = torch.empty(Bt, C, device=dev, dtype=F32)
         ops.softmax_ce(logits_masked[k - 1], pseudo, weight, self.tgt_ratio / Bt, self.loss_t, dl_t)
-        self._backward_from_logits(st_m, pooled_m, dl_t, T * n_vis)
+        # the step's LAST backward: every gradient range it completes is final, so the NCCL range all-reduces overlap it
+        self._backward_from_logits(st_m, pooled_m, dl_t, T * n_vis, grad_sync=self.grad_sync)
         self.loss.copy_(self.loss_s + self.loss_t)
         self.last = dict(attn=attn, masks=mask.view(k, frames, P).bool(), logits_s=logits_s, logits_full_t=logits_full_t,
                          logits_masked=logits_masked, clip_probs=clip_probs, sel_mask=sel.bool(), pseudo=pseudo, msp=msp)

@@ -68,7 +68,14 @@ class FinetuneCore:
         state = dict(ws=ws, pooled=pooled, normed=normed, B=B) if save else None
         return logits, state
 
-    def run_backward(self, state, g_logits):
+    def block_grad_hi(self, l):
+        """End of the decay-segment prefix that is final once block l's backward has run (head + blocks >= l)."""
+        return self.arena.range_of([f"blocks.{l}.mlp.fc2.weight", f"blocks.{l}.attn.qkv.weight"])[1]
+
+    def run_backward(self, state, g_logits, grad_sync=None):
+        """grad_sync (ddp.GradSync, world > 1): told block by block which prefix of the gradient arena is final, so that its range
+        all-reduces overlap the rest of backward (the role of DDP's buckets, run_stage2.py:641).  Only valid on the LAST
+        micro-step of an update (gradients of earlier micro-steps are already in the arena and are summed with it)."""
         a = self.arena
         a.attach_grads()
         ws, B, dev = state["ws"], state["B"], g_logits.device
@@ -81,5 +88,8 @@ class FinetuneCore:
         ops.layernorm_bwd(dy, state["pooled"], a.p32("fc_norm.weight"), self.eps, None, d_pooled, None, None, 0,
                           a.g32("fc_norm.weight"), a.g32("fc_norm.bias"))
         ops.meanpool_bwd(d_pooled, ws.dx.view(B, self.N, self.D))
-        self.trunk.backward(ws, {}, dx_init=True)
+        on_done = None
+        if grad_sync is not None and grad_sync.world > 1:
+            on_done = lambda l: grad_sync.range_ready(a.grads, self.block_grad_hi(l))
+        self.trunk.backward(ws, {}, dx_init=True, on_block_done=on_done)
         ws.busy = False
