@@ -38,6 +38,10 @@ _SIDE_WGRAD_FINE = os.environ.get("UB_SIDE_WGRAD", "0") == "2"
 # fc1 bias gradient accumulated by the epilogue of the GEMM that produces d_pre (ub_gemm_epilogue.colsum_out) instead of a
 # separate column-sum pass over d_pre: 12 launches and 12 x 63 MB of reads fewer per ViT-B step
 _FUSE_COLSUM = os.environ.get("UB_FUSE_COLSUM", "0") == "1"
+# The bias-gradient column sums of d_pre / dqkv (24 launches, ~0.35 ms per ViT-B step) feed nothing before the optimizer.  Unlike
+# the weight-gradient GEMMs they are small CTAs (256 threads, 8 KB smem, ~32 registers) that FIT BESIDE a persistent GEMM CTA on
+# the same SM, so on a side stream they run under the dgrad / wgrad GEMMs instead of between them.  UB_SIDE_COLSUM=0 turns it off.
+_SIDE_COLSUM = os.environ.get("UB_SIDE_COLSUM", "1") == "1"
 
 
 def _splits_for(out_rows: int, out_cols: int, sms: int) -> int:
@@ -124,6 +128,11 @@ class ViTTrunk:
         self.scale = 64 ** -0.5
         self.sms = ops.lib.ub_sm_count() if torch.cuda.is_available() else 148
         self._ws: Dict = {}
+
+    def _colsum_stream(self):
+        if getattr(self, "_cs", None) is None:
+            self._cs = torch.cuda.Stream(device=self.arena.device)
+        return self._cs
 
     def _side_stream(self):
         if getattr(self, "_side", None) is None:
@@ -234,11 +243,31 @@ class ViTTrunk:
             if on_block_done is not None:
                 on_block_done(l)     # every gradient of block l is final: its arena range can be all-reduced
 
+        # column sums beside the GEMMs (see _SIDE_COLSUM): cs_done[par] = the side stream has finished reading the scratch of
+        # layer parity `par`; the main stream waits for it before a later layer overwrites that scratch
+        cs = self._colsum_stream() if (_SIDE_COLSUM and side is None and ws.dx.is_cuda) else None
+        cs_main = torch.cuda.current_stream() if cs is not None else None
+        cs_done = {}
+
+        def colsum(x, out, skip=(0, 0), par=None):
+            if cs is None:
+                return ops.colsum_bf16(x, out, skip=skip)
+            ev = torch.cuda.Event()
+            ev.record(cs_main)
+            cs.wait_event(ev)
+            with torch.cuda.stream(cs):
+                ops.colsum_bf16(x, out, skip=skip)
+                done = torch.cuda.Event()
+                done.record(cs)
+            cs_done[par] = done
+
         for l in reversed(range(nl)):
             L = ws.layer(l)
             b = f"blocks.{l}."
             par = l & 1
             dxs_m, dxs_a, d_pre, dqkv = ws.dxs_m[par], ws.dxs_a[par], ws.d_pre2[par], ws.dqkv2[par]
+            if cs is not None and par in cs_done:
+                cs_main.wait_event(cs_done.pop(par))     # layer l + 2's column sums are done with d_pre / dqkv of this parity
             if side is not None and (l + 2) in side_done:
                 main.wait_event(side_done[l + 2])        # the scratch of this parity is free again
                 block_final(l + 2)
@@ -261,7 +290,7 @@ class ViTTrunk:
             ops.gemm(d_pre, self.w(b + "mlp.fc1.weight"), ws.d_h, b_t=True)
             wgrad(d_pre, L.h2, self.g(b + "mlp.fc1.weight"))
             if not _FUSE_COLSUM:
-                ops.colsum_bf16(d_pre, self.g(b + "mlp.fc1.bias"))
+                colsum(d_pre, self.g(b + "mlp.fc1.bias"), par=par)
             ops.layernorm_bwd(ws.d_h, L.x_mid, self.p(b + "norm2.weight"), self.eps, ws.dx, ws.dx, dxs_a, s_att, N,
                               self.g(b + "norm2.weight"), self.g(b + "norm2.bias"), dsum=self.g(b + "attn.proj.bias"))
             # ---- attention branch: x_mid = x_in + s * (attn(h1) Wp^T + bp)
@@ -272,7 +301,7 @@ class ViTTrunk:
             wgrad(dqkv, L.h1, self.g(b + "attn.qkv.weight"))
             # q_bias | (always-zero k gap) | v_bias are one contiguous 3D span of the gradient arena: one column-sum pass
             # over dqkv that leaves the gap alone (the key bias is structurally zero, modeling_finetune.py:104)
-            ops.colsum_bf16(dqkv, self.qkv_bias_grad(l), skip=(D, 2 * D))
+            colsum(dqkv, self.qkv_bias_grad(l), skip=(D, 2 * D), par=par)
             # next consumer of dxs: block l-1's MLP branch (unless a tap re-emits it) or the patch embedding
             emit = (l - 1) not in tap_grads
             s_next = None if (dp is None or l == 0) else dp[l - 1, 1]
@@ -289,6 +318,8 @@ class ViTTrunk:
             main.wait_stream(side)
             for l in reversed(range(min(2, nl))):
                 block_final(l)
+        if cs is not None:
+            cs_main.wait_stream(cs)          # bias gradients are complete before anything downstream (all-reduce, optimizer) runs
         # ---- patch embedding (Conv3d as GEMM): only weight and bias gradients exist
         gw = self.g("patch_embed.proj.weight")
         self._wgrad(ws.dxs_m[1], ws.patches, gw.view(D, -1))
