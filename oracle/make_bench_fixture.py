@@ -32,7 +32,8 @@ def main():
     ref = O.stage1_step(ssd, tsd, videos, q, O.StudentCfg(), O.TeacherCfg(), mask_ratio=0.8, with_grads=False)
     mask = ref["mask"].numpy().astype(np.uint8).reshape(-1)
     out = dict(loss=float(ref["loss"]), visible_tokens=int((~ref["mask"]).sum()), mask_hex=np.packbits(mask).tobytes().hex(),
-               weights_sha16=bench.weights_digest(ssd), batch=32, seed_weights=0, seed_inputs=1000,
+               weights_sha16=bench.weights_digest(ssd),
+               inputs_sha16=bench.weights_digest({"videos": videos[:1, :, :1, :64, :64].contiguous(), "q": q[:8]}), batch=32, seed_weights=0, seed_inputs=1000,
                made_by="oracle/make_bench_fixture.py", torch=torch.__version__)
     gold = os.path.join(ROOT, "tests", "golden")
     json.dump(out, open(os.path.join(gold, "bench_b32_check.json"), "w"))

@@ -112,3 +112,22 @@ def test_uint8_frames_to_normalised_patches_bit_exact(tub):
     assert torch.equal(out.cpu(), ref)
     with pytest.raises(Exception):
         ops.patchify_u8(fr.cuda()[..., :2], out, tub)          # not [.., 3]
+
+
+@pytest.mark.parametrize("variant", ["", "erf"])
+def test_gelu_epilogue_default_and_exact_erf_builds(variant):
+    """DESIGN §2: the student's GELU is evaluated with the hardware tanh.approx form (|err| <= 4.7e-4, a deliberate deviation);
+    -DUB_GELU_ERF (libunite_b200_erf.so, built by build()) restores an erf accurate to 1.5e-7.  Both builds are kept under test."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if variant:
+        assert os.path.exists(os.path.join(root, "unite_b200", "lib", f"libunite_b200_{variant}.so")), "build() did not produce the erf variant"
+    env = dict(os.environ)
+    env.pop("UB_LIB_VARIANT", None)
+    if variant:
+        env["UB_LIB_VARIANT"] = variant
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gelu_variant_check.py")], capture_output=True, text=True, env=env, timeout=300)
+    print(r.stdout[-400:])
+    assert r.returncode == 0 and "GELU VARIANT OK" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])

@@ -39,9 +39,11 @@ _SIDE_WGRAD_FINE = os.environ.get("UB_SIDE_WGRAD", "0") == "2"
 # separate column-sum pass over d_pre: 12 launches and 12 x 63 MB of reads fewer per ViT-B step
 _FUSE_COLSUM = os.environ.get("UB_FUSE_COLSUM", "0") == "1"
 # The bias-gradient column sums of d_pre / dqkv (24 launches, ~0.35 ms per ViT-B step) feed nothing before the optimizer.  Unlike
-# the weight-gradient GEMMs they are small CTAs (256 threads, 8 KB smem, ~32 registers) that FIT BESIDE a persistent GEMM CTA on
-# the same SM, so on a side stream they run under the dgrad / wgrad GEMMs instead of between them.  UB_SIDE_COLSUM=0 turns it off.
-_SIDE_COLSUM = os.environ.get("UB_SIDE_COLSUM", "1") == "1"
+# the weight-gradient GEMMs they are small CTAs (256 threads, 8 KB smem, ~32 registers); UB_SIDE_COLSUM=1 puts them on a side stream
+# so that they could run under the dgrad / wgrad GEMMs instead of between them.  Measured on B200 (A/B/A/B, 20 steps each): 17.63 /
+# 17.66 ms with, 17.71 / 17.52 ms without — no gain: a GEMM CTA holds ~227 KB of the SM's 228 KB of shared memory, so nothing
+# co-resides with it and the column sums still wait for a GEMM to drain.  Off by default.
+_SIDE_COLSUM = os.environ.get("UB_SIDE_COLSUM", "0") == "1"
 
 
 def _splits_for(out_rows: int, out_cols: int, sms: int) -> int:
