@@ -83,6 +83,10 @@ UB_API int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* 
  * Replaces modeling_finetune.py:110-116 (student Attention core) and clip.py:40-52 (nn.MultiheadAttention core);
  * ub_attn_bwd is their autograd backward (D_ws: fp32 [n_seq,H,S] scratch); ub_cls_attn is clip.py:95-96,183:
  * out[n_seq, S-1] = head-averaged softmax row of the CLS query (token 0) over the patch keys.
+ * Every S runs on tcgen05 / TMEM kernels: S <= 240 without lse (the teacher's 197-token frames) and S <= 320 with lse / backward
+ * (the student's visible tokens) keep the whole (sequence, head) item resident; longer sequences (the all-token passes of stage
+ * 2 / 3, S = 1568: modeling_finetune.py:356-383, run_stage3.py:475-483) stream K / V (or Q / dO) chunks past 128-row tiles with an
+ * online softmax forward and a two-pass backward (csrc/attention_long_tc.cu).
  * ---------------------------------------------------------------------------------------------- */
 /* diagnostic: how many 4-CTA clusters of the GEMM kernel the device can hold at once (0 = cluster-of-4 tiles are not used) */
 UB_API int ub_gemm_cluster4_capacity(void);
