@@ -536,8 +536,12 @@ def main():
             torch.cuda.synchronize()
             dist.barrier()
             torch.cuda.synchronize()
-            if os.environ.get("UB_BENCH_HARD_EXIT", "1") == "1":
-                os._exit(0)            # NCCL teardown after graph capture has hung in destroy_process_group(): leave together
+            # The fused NVLink step leaves no NCCL call inside the captured graphs, and with the graphs dropped above the process
+            # group tears down cleanly (checked at 2 GPUs).  Only the NCCL fallback path (UB_DDP_NVLS=0: all-reduces captured in
+            # the graphs) has hung in destroy_process_group(); there the ranks still leave together, hard.
+            hard = os.environ.get("UB_BENCH_HARD_EXIT", "") == "1" or (getattr(eng, "nvls", None) is None and use_graph)
+            if hard and os.environ.get("UB_BENCH_HARD_EXIT", "") != "0":
+                os._exit(0)
             dist.destroy_process_group()
 
     if rank != 0:
