@@ -101,6 +101,7 @@ def run_workload(args, rank, local, world, dev, ClockSampler, measured_peaks, F_
         workload = ("BASELINE configs[3]: stage-3 step per (source, target) pair — teacher attention on vid_aug + zero-shot CLS on vid, source "
                     "full pass (grad), target full pass, k=2 masked committee (last member trains), MatchOrConf fusion, AdamW; drop_path 0.1")
         extra["per_gpu_pairs"] = B
+        extra["ddp"] = "fused NVLink step" if getattr(eng, "nvls", None) is not None else ("NCCL all-reduce" if world > 1 else "n/a")
     else:
         from unite_b200.engine import Stage1Engine
         student, teacher = bench.build_models(seed=0, large=True)

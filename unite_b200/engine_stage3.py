@@ -46,6 +46,20 @@ class Stage3Engine:
             FusedAdamW(self.core.arena, lr, weight_decay, betas)
         self.max_norm = None
         self.grad_sync = grad_sync
+        # N > 1: the same fused NVLink step as stage 1 (the student's arena is the same; src_classifier is a separate, frozen
+        # module, run_stage3.py:1193/:1264): gradient pushes overlapped with the step's last backward, then ub_adamw_nvls
+        self.nvls = None
+        import os
+        if grad_sync is not None and getattr(grad_sync, "world", 1) > 1 and dev.type == "cuda" \
+                and os.environ.get("UB_DDP_NVLS", "1") != "0" and self.optimizer.plain_two_groups:
+            from .ddp import NvlsShardedStep
+            try:
+                self.nvls = NvlsShardedStep(self.core.arena, self.optimizer, grad_sync.pg)
+            except Exception as e:                      # no multicast / symmetric memory on this box: NCCL path
+                if os.environ.get("UB_DDP_NVLS") == "1":
+                    raise
+                import warnings
+                warnings.warn(f"unite_b200: NVLS fused optimizer step unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
         self.loss = torch.zeros(1, device=dev, dtype=F32)
         self.loss_s = torch.zeros(1, device=dev, dtype=F32)
         self.loss_t = torch.zeros(1, device=dev, dtype=F32)
@@ -142,7 +156,10 @@ class Stage3Engine:
         dl_t = torch.empty(Bt, C, device=dev, dtype=F32)
         ops.softmax_ce(logits_masked[k - 1], pseudo, weight, self.tgt_ratio / Bt, self.loss_t, dl_t)
         # the step's LAST backward: every gradient range it completes is final, so the NCCL range all-reduces overlap it
-        self._backward_from_logits(st_m, pooled_m, dl_t, T * n_vis, grad_sync=self.grad_sync)
+        hook = self.grad_sync
+        if self.nvls is not None:
+            hook = self.nvls if (self.nvls.early_push and not self.max_norm) else None
+        self._backward_from_logits(st_m, pooled_m, dl_t, T * n_vis, grad_sync=hook)
         self.loss.copy_(self.loss_s + self.loss_t)
         self.last = dict(attn=attn, masks=mask.view(k, frames, P).bool(), logits_s=logits_s, logits_full_t=logits_full_t,
                          logits_masked=logits_masked, clip_probs=clip_probs, sel_mask=sel.bool(), pseudo=pseudo, msp=msp)
@@ -151,6 +168,13 @@ class Stage3Engine:
     def step(self, videos_s, labels_s, videos_t, videos_t_aug=None):
         self.optimizer.zero_grad()
         loss = self.forward_backward(videos_s, labels_s, videos_t, videos_t_aug)
+        if self.nvls is not None:
+            self.optimizer.prepare_step(grad_scale=1.0 / self.nvls.world)
+            if self.max_norm:
+                self.nvls.step_dev_clipped(self.max_norm)
+            else:
+                self.nvls.step_dev()
+            return loss
         scale = self.grad_sync.all_reduce(self.core.arena.grads) if self.grad_sync is not None else 1.0
         self.optimizer.step(grad_scale=scale, max_norm=self.max_norm)
         return loss
@@ -180,7 +204,12 @@ def _engine_for(model, teacher_model, src_classifier, optimizer, mask_ratio, arg
         return eng
     eng = held[2]
     if optimizer is not None and optimizer is not eng.optimizer:
-        eng.optimizer = require_fused_optimizer(optimizer, eng.core.arena, "train_one_epoch")
+        new = require_fused_optimizer(optimizer, eng.core.arena, "train_one_epoch")
+        if eng.nvls is not None:
+            if not new.plain_two_groups:
+                raise NotImplementedError("the fused NVLink step updates the plain [decay | no-decay] layout (UB_DDP_NVLS=0 otherwise)")
+            eng.nvls.opt, new.gnorm_sq, new._sharded = new, eng.optimizer.gnorm_sq, eng.nvls
+        eng.optimizer = new
     eng.mask_ratio = mask_ratio
     return eng
 
