@@ -433,3 +433,39 @@ def test_full_vitb16_stage2_all_tokens_against_oracle():
         worst_c, worst_r = min(worst_c, c), max(worst_r, r)
         assert c >= 0.999 and r <= 2e-2, (k, c, r)
     print(f"stage-2 full size grads: worst cosine {worst_c:.6f}, worst rel-L2 {worst_r:.2e}")
+
+
+# ---- several optimizer steps in a row: the whole loop (forward, backward, AdamW, bf16 shadow refresh) tracks the reference ---------
+def test_four_training_steps_track_the_oracle_with_torch_adamw():
+    """run_stage1.py:360-456 repeated: oracle step -> torch.optim.AdamW (decay / no-decay groups, optim_factory.py:76-118) on the CPU
+    against Stage1Engine.step (with the CUDA graph: steps 3 and 4 are replays).  Losses within 1e-3 at every step, weights after the
+    last step within 2e-3 relative (bf16 operands perturb each step's gradient by <= 2e-2 relative; Adam's normalised update turns
+    that into a small fraction of lr per step)."""
+    from oracle import unite_oracle as O
+    from unite_b200.engine import Stage1Engine
+    fix, scfg, tcfg, ssd, tsd, _, student, teacher = _tiny()
+    student.eval()                                                                  # no DropPath in this trajectory
+    B, lr, wd = 8, 2e-3, 0.05
+    batches = [_tiny_batch(scfg, B, 100 + i) for i in range(2)]
+    ps = {k: v.clone().requires_grad_() for k, v in ssd.items()}
+    dec = [p for k, p in ps.items() if not (p.ndim == 1 or k.endswith(".bias"))]
+    nod = [p for k, p in ps.items() if (p.ndim == 1 or k.endswith(".bias"))]
+    opt = torch.optim.AdamW([dict(params=dec, weight_decay=wd), dict(params=nod, weight_decay=0.0)], lr=lr, betas=(0.9, 0.95), eps=1e-8)
+    eng = Stage1Engine(student, teacher, mask_ratio=fix["cfg"]["mask_ratio"], lr=lr, weight_decay=wd, use_graph=True)
+    dev_batches = [(v.cuda(), q.cuda()) for v, q in batches]
+    for it in range(4):
+        v, q = batches[it % 2]
+        cur = {k: p.detach() for k, p in ps.items()}
+        ref = O.stage1_step(cur, tsd, v, q, scfg, tcfg, mask_ratio=fix["cfg"]["mask_ratio"])
+        for k, p in ps.items():
+            p.grad = ref["grads"][k]
+        opt.step()
+        loss = eng.step(*dev_batches[it % 2]).item()
+        rel = abs(loss - ref["loss"].item()) / abs(ref["loss"].item())
+        print(f"step {it}: loss {loss:.6f} vs {ref['loss'].item():.6f} ({rel:.1e})")
+        assert rel < LOSS_TOL, (it, loss, ref["loss"].item())
+    assert len(eng._graphs) >= 1
+    sd = student.state_dict()
+    worst = max(rel_l2(sd[k], p) for k, p in ps.items() if p.numel() >= 4096)
+    print(f"weights after 4 steps: worst rel-L2 {worst:.2e}")
+    assert worst < 2e-3
