@@ -22,7 +22,8 @@ def test_tokens_patchify_mask_gather_bit_exact():
     m = _kc(); m.check_tokens(); assert m.OK
 
 
-@pytest.mark.parametrize("rows,D", [(4096, 768), (1024, 128), (512, 1024)])
+# (10240, 768), (5003, 1024), (6000, 256): large enough for the bulk-copy-staged backward (ragged last row block included)
+@pytest.mark.parametrize("rows,D", [(4096, 768), (1024, 128), (512, 1024), (10240, 768), (5008, 1024), (6000, 256)])
 def test_layernorm_family(rows, D):
     m = _kc(); m.check_ln(rows, D); assert m.OK
 

@@ -224,6 +224,13 @@ UB_DEVINL void tma_load_3d(const CUtensorMap* m, uint64_t* bar, void* dst, int c
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (no tensor map): `bytes` must be a multiple of 16, both addresses 16-byte aligned
+UB_DEVINL void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // L2 prefetch of a tile (no smem, no completion tracking)
 UB_DEVINL void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
