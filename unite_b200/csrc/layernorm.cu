@@ -163,76 +163,6 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnFwdArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward, contiguous rows, staged through shared memory by bulk copies (same scheme as ln_bwd_staged_kernel below): two CTAs of
-// 8 warps per SM, each with a 4-deep ring of 8-row blocks, so ~150 KB of loads are outstanding per SM whatever the warps are
-// doing.  The register kernel above has one row per warp in flight and measured 10-13 us for the student's 47 MB (latency bound).
-// ------------------------------------------------------------------------------------------------
-constexpr int LNF_ROWS = 8, LNF_STAGES = 4;
-template <int NV, bool XF16>
-__global__ void __launch_bounds__(256, 2) ln_fwd_staged_kernel(const LnFwdArgs a) {
-  pdl_grid_sync();
-  extern __shared__ __align__(128) uint8_t lnf_smem[];
-  constexpr int D = NV * 128;
-  constexpr int ESZ = XF16 ? 2 : 4;
-  constexpr int STAGE = LNF_ROWS * D * ESZ;
-  uint64_t* full = reinterpret_cast<uint64_t*>(lnf_smem + LNF_STAGES * STAGE);
-  uint64_t* empty = full + LNF_STAGES;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int nv = NV;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < LNF_STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], LNF_ROWS);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-  const int n_blocks = (a.rows + LNF_ROWS - 1) / LNF_ROWS;
-  const uint8_t* gx = reinterpret_cast<const uint8_t*>(a.x);
-  auto request = [&](int j) {
-    const int blk = blockIdx.x + j * gridDim.x;
-    if (blk >= n_blocks) return;
-    const int st = j % LNF_STAGES;
-    mbar_wait(&empty[st], (uint32_t)((j / LNF_STAGES) & 1) ^ 1u);
-    const int row0 = blk * LNF_ROWS, nr = min(LNF_ROWS, a.rows - row0);
-    const uint32_t bytes = (uint32_t)nr * D * ESZ;
-    mbar_expect_tx(&full[st], bytes);
-    bulk_load_1d(lnf_smem + (size_t)st * STAGE, gx + (int64_t)row0 * D * ESZ, bytes, &full[st]);
-  };
-  if (threadIdx.x == 0)
-    for (int j = 0; j < LNF_STAGES - 1; ++j) request(j);
-  int it = 0;
-  for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
-    const int st = it % LNF_STAGES;
-    const int row = blk * LNF_ROWS + warp;
-    if (threadIdx.x == 0) request(it + LNF_STAGES - 1);
-    __syncwarp();
-    mbar_wait(&full[st], (uint32_t)((it / LNF_STAGES) & 1));
-    RowT<NV> x;
-    if (row < a.rows) {
-      const uint8_t* src = lnf_smem + (size_t)st * STAGE + (size_t)warp * D * ESZ;
-      if (XF16) row_load_f16(x, reinterpret_cast<const __half*>(src), nv, lane);
-      else row_load_f32(x, reinterpret_cast<const float*>(src), nv, lane);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[st]);
-    if (row >= a.rows) continue;
-    const float rstd = row_center_rstd(x, nv, D, a.eps);
-    UB_ROW_FOREACH(i, nv) {
-      float4 g, b;
-      asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g.x), "=f"(g.y), "=f"(g.z), "=f"(g.w) : "l"(a.gamma + (i * 32 + lane) * 4));
-      asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(a.beta + (i * 32 + lane) * 4));
-      x.v[i].x = x.v[i].x * rstd * g.x + b.x;
-      x.v[i].y = x.v[i].y * rstd * g.y + b.y;
-      x.v[i].z = x.v[i].z * rstd * g.z + b.z;
-      x.v[i].w = x.v[i].w * rstd * g.w + b.w;
-    }
-    if (a.out_fp32) row_store_f32(x, reinterpret_cast<float*>(a.out) + (int64_t)row * D, nv, lane);
-    else row_store_bf16(x, reinterpret_cast<bf16*>(a.out) + (int64_t)row * D, nv, lane);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // teacher token assembly + ln_pre (clip.py:150-152): row (f, tok):  tok==0 ? cls : E[f*P + tok-1], + pos[tok], LN
 // ------------------------------------------------------------------------------------------------
 template <int NV>
@@ -682,37 +612,8 @@ extern "C" int ub_layernorm_fwd(const void* x, int x_f16, const int* src_rows, c
   UB_REQUIRE((post_add == nullptr) == (post_idx == nullptr), "layernorm_fwd: post_add and post_idx go together");
   if (check_D(D, "layernorm_fwd")) return 1;
   LnFwdArgs a{x, src_rows, gamma, beta, post_add, post_idx, out, out_fp32, rows, D, eps, x_f16};
-  static int use_staged = -1;
-  if (use_staged < 0) {
-    const char* e = getenv("UB_LN_FWD_STAGED");
-    use_staged = e ? atoi(e) : 1;
-  }
-  if (use_staged && src_rows == nullptr && post_add == nullptr && rows >= 4 * LNF_ROWS * sm_count() && D >= 256) {
-    // contiguous rows, large input: bulk-copy-staged kernel, two CTAs per SM
-    const size_t smem = (size_t)LNF_STAGES * LNF_ROWS * D * (x_f16 ? 2 : 4) + 2 * LNF_STAGES * sizeof(uint64_t) + 16;
-    const int n_blocks = (rows + LNF_ROWS - 1) / LNF_ROWS;
-    const int grid = n_blocks < 2 * sm_count() ? n_blocks : 2 * sm_count();
-    cudaStream_t st = (cudaStream_t)stream;
-#define UB_LNF_CASE(NVV)                                                                                                       \
-  case NVV: {                                                                                                                  \
-    static bool cfg = false;                                                                                                   \
-    if (!cfg) {                                                                                                                \
-      const int big = LNF_STAGES * LNF_ROWS * NVV * 128 * 4 + 2 * LNF_STAGES * 8 + 16;                                          \
-      cudaError_t e1 = cudaFuncSetAttribute(ln_fwd_staged_kernel<NVV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
-      cudaError_t e2 = cudaFuncSetAttribute(ln_fwd_staged_kernel<NVV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);  \
-      UB_REQUIRE(e1 == cudaSuccess && e2 == cudaSuccess, "cudaFuncSetAttribute(ln_fwd_staged smem=%d) failed", big);            \
-      cfg = true;                                                                                                              \
-    }                                                                                                                          \
-    if (x_f16) UB_LAUNCH((ln_fwd_staged_kernel<NVV, true>), grid, 256, smem, st, a);                                            \
-    else UB_LAUNCH((ln_fwd_staged_kernel<NVV, false>), grid, 256, smem, st, a);                                                 \
-  } break;
-    switch (D >> 7) {
-      UB_LNF_CASE(2) UB_LNF_CASE(4) UB_LNF_CASE(6) UB_LNF_CASE(8)
-      default: break;
-    }
-#undef UB_LNF_CASE
-    return check_launch("ln_fwd_staged_kernel");
-  }
+  // (a bulk-copy-staged forward like ln_bwd_staged_kernel was measured and dropped: 0.58-0.72 ms per step against 0.51-0.58 ms for
+  // this kernel — a 10 us launch over 47 MB does not amortise the ring's set-up)
   UB_LN_DISPATCH(D, ln_fwd_kernel, ln_grid(rows), 0, (cudaStream_t)stream, a)
   return check_launch("ln_fwd_kernel");
 }
