@@ -93,7 +93,10 @@ UB_API int ub_gemm_cluster4_capacity(void);
 
 UB_API int ub_attn_fwd(const void* qkv, void* o, float* lse /* may be NULL */, int n_seq, int S, int H, float scale,
                        void* stream);
-UB_API int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* D_ws, void* dqkv,
+/* dbias (may be NULL): fp32 [3*H*64], += the column sums over all rows of the dq and dv thirds of dqkv — the q_bias / v_bias
+ * gradients of modeling_finetune.py:104-108 (the key third has no bias and is left untouched) — accumulated by the kernels as they
+ * store dqkv, which saves the separate pass over it. */
+UB_API int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* D_ws, void* dqkv, float* dbias,
                        int n_seq, int S, int H, float scale, void* stream);
 UB_API int ub_cls_attn(const void* qkv, float* out, int n_seq, int S, int H, float scale, void* stream);
 

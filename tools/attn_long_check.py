@@ -69,12 +69,16 @@ def check(n_seq, S, H, amp=0.7, spike=False, time_it=False, no_lse=False):
     oref.backward(d_o.float().view(n_seq, S, H, 64).permute(0, 2, 1, 3))
     dqkv = torch.full_like(qkv, float("nan"))
     dws = torch.empty(n_seq, H, S, device=dev)
-    ops.attn_bwd(qkv, o, d_o, lse, dws, dqkv, n_seq, S, H, scale)
+    dbias = torch.zeros(3 * H * 64, device=dev)
+    ops.attn_bwd(qkv, o, d_o, lse, dws, dqkv, n_seq, S, H, scale, dbias=dbias)
     torch.cuda.synchronize()
     dq, dk, dv = dqkv.float().view(n_seq, S, 3, H, 64).permute(2, 0, 3, 1, 4)
     report(f"bwd dq  {tag}", dq, q.grad, 1.2e-2)
     report(f"bwd dk  {tag}", dk, k.grad, 1.2e-2)
     report(f"bwd dv  {tag}", dv, v.grad, 1.2e-2)
+    want = dqkv.float().sum(0)                      # bias gradients = column sums of the bf16 dqkv as stored; key third untouched
+    want[H * 64:2 * H * 64] = 0
+    report(f"bwd dbias {tag}", dbias, want, 1e-4)
     if time_it:
         fl = 4.0 * S * S * 64 * H * n_seq
         t = timeit(lambda: ops.attn_fwd(qkv, o, lse, n_seq, S, H, scale))

@@ -47,11 +47,15 @@ def check_attention(n_seq, S, H, time_it=False):
     oref.backward(d_o.float().view(n_seq, S, H, 64).permute(0, 2, 1, 3))
     dqkv = torch.zeros_like(qkv)
     dws = torch.empty(n_seq, H, S, device=dev)
-    ops.attn_bwd(qkv, o, d_o, lse, dws, dqkv, n_seq, S, H, scale)
+    dbias = torch.zeros(3 * H * 64, device=dev)
+    ops.attn_bwd(qkv, o, d_o, lse, dws, dqkv, n_seq, S, H, scale, dbias=dbias)
     dq, dk, dv = dqkv.float().view(n_seq, S, 3, H, 64).permute(2, 0, 3, 1, 4)
     report(f"attn_bwd dq  S={S} H={H}", dq, q.grad, 1.2e-2)
     report(f"attn_bwd dk  S={S} H={H}", dk, k.grad, 1.2e-2)
     report(f"attn_bwd dv  S={S} H={H}", dv, v.grad, 1.2e-2)
+    want = dqkv.float().sum(0)
+    want[H * 64:2 * H * 64] = 0
+    report(f"attn_bwd dbias S={S} H={H}", dbias, want, 1e-4)
     # cls attention
     att = torch.empty(n_seq, S - 1, device=dev)
     ops.cls_attn(qkv, att, n_seq, S, H, scale)

@@ -60,7 +60,7 @@ SIGNATURES = {
     "ub_gemm_cluster4_capacity": (C.c_int, []),
     "ub_gemm_bf16": (C.c_int, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, C.POINTER(GemmEpilogue), _I, _P]),
     "ub_attn_fwd": (C.c_int, [_P, _P, _P, _I, _I, _I, _F, _P]),
-    "ub_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "ub_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "ub_cls_attn": (C.c_int, [_P, _P, _I, _I, _I, _F, _P]),
     "ub_layernorm_fwd": (C.c_int, [_P, _I, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P]),
     "ub_teacher_embed_ln": (C.c_int, [_P, _P, _P, _P, _P, _F, _P, _I, _P, _I, _I, _I, _P]),

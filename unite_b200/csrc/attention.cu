@@ -558,11 +558,11 @@ __global__ void cls_attn_kernel(const bf16* __restrict__ qkv, float* __restrict_
 namespace ub {
 int launch_attn_fwd_tc(const void* qkv, void* o, int n_seq, int S, int H, float scale, cudaStream_t stream);
 int launch_attn_fwd_lse_tc(const void* qkv, void* o, float* lse, int n_seq, int S, int H, float scale, cudaStream_t stream);
-int launch_attn_bwd_tc(const void* qkv, const void* d_o, const float* lse, const float* Dv, void* dqkv, int n_seq, int S, int H,
-                       float scale, cudaStream_t stream);
+int launch_attn_bwd_tc(const void* qkv, const void* d_o, const float* lse, const float* Dv, void* dqkv, float* dbias, int n_seq, int S,
+                       int H, float scale, cudaStream_t stream);
 int launch_attn_fwd_long_tc(const void* qkv, void* o, float* lse, int n_seq, int S, int H, float scale, cudaStream_t stream);
-int launch_attn_bwd_long_tc(const void* qkv, const void* d_o, const float* lse, const float* Dv, void* dqkv, int n_seq, int S, int H,
-                            float scale, cudaStream_t stream);
+int launch_attn_bwd_long_tc(const void* qkv, const void* d_o, const float* lse, const float* Dv, void* dqkv, float* dbias, int n_seq, int S,
+                            int H, float scale, cudaStream_t stream);
 // UB_ATTN_LONG_TC=0: fall back to the mma.sync kernels below for S beyond the short-sequence tcgen05 kernels (debugging only)
 static bool use_long_tc() {
   static int v = -1;
@@ -601,7 +601,7 @@ extern "C" int ub_attn_fwd(const void* qkv, void* o, float* lse, int n_seq, int 
   return check_launch("attn_fwd_kernel");
 }
 
-extern "C" int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* D_ws, void* dqkv,
+extern "C" int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* D_ws, void* dqkv, float* dbias,
                            int n_seq, int S, int H, float scale, void* stream) {
   UB_REQUIRE(qkv && o && d_o && lse && D_ws && dqkv, "attn_bwd: null pointer");
   UB_REQUIRE(n_seq > 0 && S > 0 && H > 0, "attn_bwd: bad shape n_seq=%d S=%d H=%d", n_seq, S, H);
@@ -616,8 +616,8 @@ extern "C" int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, cons
     const char* e = getenv("UB_ATTN_BWD_TC");
     use_tc = e ? atoi(e) : 1;
   }
-  if (use_tc && S <= 320) return launch_attn_bwd_tc(qkv, d_o, lse, D_ws, dqkv, n_seq, S, H, scale, st);
-  if (use_long_tc()) return launch_attn_bwd_long_tc(qkv, d_o, lse, D_ws, dqkv, n_seq, S, H, scale, st);
+  if (use_tc && S <= 320) return launch_attn_bwd_tc(qkv, d_o, lse, D_ws, dqkv, dbias, n_seq, S, H, scale, st);
+  if (use_long_tc()) return launch_attn_bwd_long_tc(qkv, d_o, lse, D_ws, dqkv, dbias, n_seq, S, H, scale, st);
   dim3 grid((S + TQ - 1) / TQ, H, n_seq);
   constexpr int SMEM_DKV = 6 * TQ * 128 + 4 * TQ * 4;
   constexpr int SMEM_DQ = 6 * TQ * 128;
@@ -631,7 +631,10 @@ extern "C" int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, cons
   UB_LAUNCH(attn_bwd_dkv_kernel, grid, 128, SMEM_DKV, st, (const bf16*)qkv, (const bf16*)d_o, lse, D_ws, (bf16*)dqkv, S, H, scale);
   if (check_launch("attn_bwd_dkv_kernel")) return 1;
   UB_LAUNCH(attn_bwd_dq_kernel, grid, 128, SMEM_DQ, st, (const bf16*)qkv, (const bf16*)d_o, lse, D_ws, (bf16*)dqkv, S, H, scale);
-  return check_launch("attn_bwd_dq_kernel");
+  if (check_launch("attn_bwd_dq_kernel")) return 1;
+  if (dbias != nullptr)        // the mma.sync fallback has no fused bias gradient: one column-sum pass over dqkv, key third skipped
+    return ub_colsum_bf16(dqkv, 3 * (int64_t)H * 64, dbias, n_seq * S, 3 * H * 64, H * 64, 2 * H * 64, stream);
+  return 0;
 }
 
 extern "C" int ub_cls_attn(const void* qkv, float* out, int n_seq, int S, int H, float scale, void* stream) {

@@ -45,6 +45,7 @@ constexpr int ABT_SMEM = ABT_BAR + ABT_NBAR * 8 + 16;
 struct AttnBwdTcParams {
   const float* lse;
   const float* Dv;
+  float* dbias;             // optional fp32 [3*H*64]: += column sums of the dq and dv written (the q_bias / v_bias gradients)
   int n_seq, S, H;
   int nkt, nc, nb, ntile;   // key tiles (128), query chunks (32), Q/dO boxes (64 rows), query tiles (128)
   float sl2, scale;
@@ -251,7 +252,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint32_t set = 0, ph = 0, par = 0;     // TMEM set (n % 3), its phase ((n / 3) & 1) and owner warpgroup (n & 1) of chunk n
     uint32_t kvn = 0;
     // TMEM (32 rows x 64 fp32 columns at t_src) -> * mul -> bf16 -> swizzled slab -> TMA store at (col, row, seq)
-    auto store_tile = [&](uint32_t t_src, float mul, int col, int row, int seq) {
+    auto store_tile = [&](uint32_t t_src, float mul, int col, int row, int seq, float* bias_dst) {
       if (lane == 0) tma_store_wait_read<0>();
       __syncwarp();
 #pragma unroll
@@ -276,6 +277,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (lane == 0 && row < p.S) {
         tma_store_3d(&tmOut, stg, col, row, seq);
         tma_store_commit();
+      }
+      if (bias_dst != nullptr) {
+        // bias gradient of these 64 columns: column sums of the bf16 slab just written (rows past the sequence end are exact
+        // zeros); lane l owns columns 2l, 2l+1 — every lane reads 4 B of the same swizzled 128-byte row: conflict-free
+        float c0 = 0.f, c1 = 0.f;
+        const uint32_t chunk = (uint32_t)(lane >> 2), within = (uint32_t)(lane & 3) * 4u;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          uint32_t u;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(stg_a + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4) + within));
+          const float2 f = unpack_bf16x2(u);
+          c0 += f.x; c1 += f.y;
+        }
+        atomicAdd(bias_dst + 2 * lane, c0);
+        atomicAdd(bias_dst + 2 * lane + 1, c1);
       }
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -345,8 +361,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           mbar_wait(dkv_full, kvn & 1);
           tc_fence_after();
           const int row = kt * 128 + sp * 32;
-          if (g == 0) store_tile(t_lane + TM_DV, 1.0f, (2 * p.H + h) * 64, row, seq);
-          else store_tile(t_lane + TM_DK, p.scale, (p.H + h) * 64, row, seq);
+          if (g == 0) store_tile(t_lane + TM_DV, 1.0f, (2 * p.H + h) * 64, row, seq, p.dbias ? p.dbias + (2 * p.H + h) * 64 : nullptr);
+          else store_tile(t_lane + TM_DK, p.scale, (p.H + h) * 64, row, seq, nullptr);     // the key bias is structurally zero
           if (lane == 0) mbar_arrive(dkv_free);
         }
       }
@@ -354,7 +370,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // ---- dQ of the item
       mbar_wait(dq_full, it & 1);
       tc_fence_after();
-      for (int t = g; t < p.ntile; t += 2) store_tile(t_lane + TM_DQ + t * 64, p.scale, h * 64, t * 128 + sp * 32, seq);
+      for (int t = g; t < p.ntile; t += 2)
+        store_tile(t_lane + TM_DQ + t * 64, p.scale, h * 64, t * 128 + sp * 32, seq, p.dbias ? p.dbias + h * 64 : nullptr);
       if (lane == 0) {
         mbar_arrive(dq_free);
         mbar_arrive(&ld_empty[it & 1]);
@@ -371,11 +388,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // D = rowsum(dO o O) is produced by attn_bwd_prep_kernel (attention.cu) before this launch.
-int launch_attn_bwd_tc(const void* qkv, const void* d_o, const float* lse, const float* Dv, void* dqkv, int n_seq, int S, int H,
-                       float scale, cudaStream_t stream) {
+int launch_attn_bwd_tc(const void* qkv, const void* d_o, const float* lse, const float* Dv, void* dqkv, float* dbias, int n_seq, int S,
+                       int H, float scale, cudaStream_t stream) {
   UB_REQUIRE(S <= ABT_MAX_S, "attn_bwd_tc: S=%d exceeds %d", S, ABT_MAX_S);
   AttnBwdTcParams p;
-  p.lse = lse; p.Dv = Dv;
+  p.lse = lse; p.Dv = Dv; p.dbias = dbias;
   p.n_seq = n_seq; p.S = S; p.H = H;
   p.nkt = (S + 127) / 128;
   p.nc = (S + 31) / 32;

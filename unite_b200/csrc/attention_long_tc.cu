@@ -58,6 +58,7 @@ struct AttnLongParams {
   float* lse_out;        // FWD: [n_seq, H, S] or null
   const float* lse;      // DQ / DKV
   const float* Dv;       // DQ / DKV: rowsum(dO o O)
+  float* dbias;          // DQ / DKV, optional fp32 [3*H*64]: += column sums of the dq / dv written (q_bias / v_bias gradients)
   int n_seq, S, H;
   int ntile, npair, nchunk;
   float sl2, scale;
@@ -275,7 +276,7 @@ attn_long_tc_kernel(const __grid_constant__ CUtensorMap tmStat, const __grid_con
     const uint32_t sw = (uint32_t)(lane & 7);
     const float sl2 = p.sl2;
     // TMEM (32 rows x 64 fp32 columns at t_src) -> * mul -> bf16 -> swizzled slab -> TMA store at (col, row, seq)
-    auto store_tile = [&](uint32_t t_src, float mul, int col, int row, int seq, bool active) {
+    auto store_tile = [&](uint32_t t_src, float mul, int col, int row, int seq, bool active, float* bias_dst) {
       if (lane == 0) tma_store_wait_read<0>();
       __syncwarp();
 #pragma unroll
@@ -300,6 +301,23 @@ attn_long_tc_kernel(const __grid_constant__ CUtensorMap tmStat, const __grid_con
       if (lane == 0 && active && row < p.S) {
         tma_store_3d(&tmOut, stg, col, row, seq);
         tma_store_commit();
+      }
+      if (bias_dst != nullptr && active) {
+        // bias gradient of these 64 columns = column sums of the bf16 slab just written.  Rows past the sequence end are exact
+        // zeros in the DKV pass (zero-filled K / V rows give zero dK / dV rows only if P^T is zero there: it is not — so those
+        // rows are masked here) and in the DQ pass (zero Q / dO rows: dS row = P (0 - 0) = 0).
+        float c0 = 0.f, c1 = 0.f;
+        const uint32_t chunk = (uint32_t)(lane >> 2), within = (uint32_t)(lane & 3) * 4u;
+        const int valid = min(32, p.S - row);
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          uint32_t u;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(stg_a + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4) + within));
+          const float2 f = unpack_bf16x2(u);
+          if (r < valid) { c0 += f.x; c1 += f.y; }
+        }
+        atomicAdd(bias_dst + 2 * lane, c0);
+        atomicAdd(bias_dst + 2 * lane + 1, c1);
       }
     };
     // The TMEM read port (64 B/clk/SM) bounds every mode (4 B of scores per (query, key) pair forward, 8 B backward), with the
@@ -462,12 +480,12 @@ attn_long_tc_kernel(const __grid_constant__ CUtensorMap tmStat, const __grid_con
         tmem_ld_wait();
         const float l = __uint_as_float(lsum);
         if (p.lse_out != nullptr && active && row < p.S) p.lse_out[(int64_t)item * p.S + row] = ref * p.scale + __logf(l);
-        store_tile(t_row + 128, 1.0f / l, h * 64, row0, seq, active);
+        store_tile(t_row + 128, 1.0f / l, h * 64, row0, seq, active, nullptr);
       } else if (MODE == AL_DQ) {
-        store_tile(t_row + 128, p.scale, h * 64, row0, seq, active);
+        store_tile(t_row + 128, p.scale, h * 64, row0, seq, active, p.dbias ? p.dbias + h * 64 : nullptr);
       } else {
-        store_tile(t_row + 128, 1.0f, (2 * p.H + h) * 64, row0, seq, active);
-        store_tile(t_row + 192, p.scale, (p.H + h) * 64, row0, seq, active);
+        store_tile(t_row + 128, 1.0f, (2 * p.H + h) * 64, row0, seq, active, p.dbias ? p.dbias + (2 * p.H + h) * 64 : nullptr);
+        store_tile(t_row + 192, p.scale, (p.H + h) * 64, row0, seq, active, nullptr);
       }
       if (lane == 0) mbar_arrive(&acc_free[g]);
     }
@@ -485,11 +503,11 @@ attn_long_tc_kernel(const __grid_constant__ CUtensorMap tmStat, const __grid_con
 }
 
 template <int MODE>
-static int launch_attn_long(const void* qkv, const void* d_o, void* out, float* lse_out, const float* lse, const float* Dv, int n_seq,
-                            int S, int H, float scale, cudaStream_t stream) {
+static int launch_attn_long(const void* qkv, const void* d_o, void* out, float* lse_out, const float* lse, const float* Dv, float* dbias,
+                            int n_seq, int S, int H, float scale, cudaStream_t stream) {
   using C = ALC<MODE>;
   AttnLongParams p;
-  p.lse_out = lse_out; p.lse = lse; p.Dv = Dv;
+  p.lse_out = lse_out; p.lse = lse; p.Dv = Dv; p.dbias = dbias;
   p.n_seq = n_seq; p.S = S; p.H = H;
   p.ntile = (S + 127) / 128;
   p.npair = (p.ntile + 1) / 2;
@@ -523,14 +541,14 @@ static int launch_attn_long(const void* qkv, const void* d_o, void* out, float* 
 }
 
 int launch_attn_fwd_long_tc(const void* qkv, void* o, float* lse, int n_seq, int S, int H, float scale, cudaStream_t stream) {
-  return launch_attn_long<AL_FWD>(qkv, nullptr, o, lse, nullptr, nullptr, n_seq, S, H, scale, stream);
+  return launch_attn_long<AL_FWD>(qkv, nullptr, o, lse, nullptr, nullptr, nullptr, n_seq, S, H, scale, stream);
 }
 
 // D = rowsum(dO o O) is produced by attn_bwd_prep_kernel (attention.cu) before this call
-int launch_attn_bwd_long_tc(const void* qkv, const void* d_o, const float* lse, const float* Dv, void* dqkv, int n_seq, int S, int H,
-                            float scale, cudaStream_t stream) {
-  if (launch_attn_long<AL_DKV>(qkv, d_o, dqkv, nullptr, lse, Dv, n_seq, S, H, scale, stream)) return 1;
-  return launch_attn_long<AL_DQ>(qkv, d_o, dqkv, nullptr, lse, Dv, n_seq, S, H, scale, stream);
+int launch_attn_bwd_long_tc(const void* qkv, const void* d_o, const float* lse, const float* Dv, void* dqkv, float* dbias, int n_seq, int S,
+                            int H, float scale, cudaStream_t stream) {
+  if (launch_attn_long<AL_DKV>(qkv, d_o, dqkv, nullptr, lse, Dv, dbias, n_seq, S, H, scale, stream)) return 1;
+  return launch_attn_long<AL_DQ>(qkv, d_o, dqkv, nullptr, lse, Dv, dbias, n_seq, S, H, scale, stream);
 }
 
 }  // namespace ub

@@ -44,6 +44,9 @@ _FUSE_COLSUM = os.environ.get("UB_FUSE_COLSUM", "0") == "1"
 # 17.66 ms with, 17.71 / 17.52 ms without — no gain: a GEMM CTA holds ~227 KB of the SM's 228 KB of shared memory, so nothing
 # co-resides with it and the column sums still wait for a GEMM to drain.  Off by default.
 _SIDE_COLSUM = os.environ.get("UB_SIDE_COLSUM", "0") == "1"
+# q_bias / v_bias gradients accumulated by the attention backward kernels while they store dq / dv (ub_attn_bwd's dbias) instead
+# of a separate column-sum pass over dqkv: 12 launches fewer per ViT-B step.  UB_FUSE_QKV_BIAS=0 restores the separate pass.
+_FUSE_QKV_BIAS = os.environ.get("UB_FUSE_QKV_BIAS", "1") == "1"
 
 
 def _splits_for(out_rows: int, out_cols: int, sms: int) -> int:
@@ -298,12 +301,14 @@ class ViTTrunk:
             # ---- attention branch: x_mid = x_in + s * (attn(h1) Wp^T + bp)
             ops.gemm(dxs_a, self.w(b + "attn.proj.weight"), ws.d_o, b_t=True)
             wgrad(dxs_a, L.o, self.g(b + "attn.proj.weight"))
-            ops.attn_bwd(L.qkv, L.o, ws.d_o, L.lse, ws.d_ws, dqkv, ws.B, N, self.H, self.scale)
+            # q_bias | (always-zero k gap) | v_bias are one contiguous 3D span of the gradient arena; the attention backward adds the
+            # column sums of dq and dv into it as it stores them (the key bias is structurally zero, modeling_finetune.py:104)
+            ops.attn_bwd(L.qkv, L.o, ws.d_o, L.lse, ws.d_ws, dqkv, ws.B, N, self.H, self.scale,
+                         dbias=self.qkv_bias_grad(l) if _FUSE_QKV_BIAS else None)
             ops.gemm(dqkv, self.w(b + "attn.qkv.weight"), ws.d_h, b_t=True)
             wgrad(dqkv, L.h1, self.g(b + "attn.qkv.weight"))
-            # q_bias | (always-zero k gap) | v_bias are one contiguous 3D span of the gradient arena: one column-sum pass
-            # over dqkv that leaves the gap alone (the key bias is structurally zero, modeling_finetune.py:104)
-            colsum(dqkv, self.qkv_bias_grad(l), skip=(D, 2 * D), par=par)
+            if not _FUSE_QKV_BIAS:
+                colsum(dqkv, self.qkv_bias_grad(l), skip=(D, 2 * D), par=par)
             # next consumer of dxs: block l-1's MLP branch (unless a tap re-emits it) or the patch embedding
             emit = (l - 1) not in tap_grads
             s_next = None if (dp is None or l == 0) else dp[l - 1, 1]
