@@ -278,17 +278,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_store_3d(&tmOut, stg, col, row, seq);
         tma_store_commit();
       }
-      if (bias_dst != nullptr) {
-        // bias gradient of these 64 columns: column sums of the bf16 slab just written (rows past the sequence end are exact
-        // zeros); lane l owns columns 2l, 2l+1 — every lane reads 4 B of the same swizzled 128-byte row: conflict-free
+      if (bias_dst != nullptr && row < p.S) {
+        // bias gradient of these 64 columns: column sums of the bf16 slab just written, rows of the sequence only (a dQ tile's
+        // rows past the last query chunk are whatever the never-written part of the dS^T staging held); lane l owns columns
+        // 2l, 2l+1 — every lane reads 4 B of the same swizzled 128-byte row: conflict-free
         float c0 = 0.f, c1 = 0.f;
         const uint32_t chunk = (uint32_t)(lane >> 2), within = (uint32_t)(lane & 3) * 4u;
+        const int valid = min(32, p.S - row);
 #pragma unroll 8
         for (int r = 0; r < 32; ++r) {
           uint32_t u;
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(stg_a + (uint32_t)r * 128u + ((chunk ^ (uint32_t)(r & 7)) << 4) + within));
           const float2 f = unpack_bf16x2(u);
-          c0 += f.x; c1 += f.y;
+          if (r < valid) { c0 += f.x; c1 += f.y; }
         }
         atomicAdd(bias_dst + 2 * lane, c0);
         atomicAdd(bias_dst + 2 * lane + 1, c1);
