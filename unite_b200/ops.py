@@ -144,6 +144,9 @@ def attn_bwd(qkv, o, d_o, lse, d_ws, dqkv, n_seq, S, H, scale, dbias=None):
     """dbias: optional fp32 [3*H*64], += column sums of the dq / dv thirds of dqkv (q_bias / v_bias gradients; the key third is untouched)."""
     if dbias is not None and dbias.numel() != 3 * H * 64:
         raise _cabi.UBError("attn_bwd dbias: fp32 [3*H*64] expected")
+    if S <= 320:
+        global LAUNCHES
+        LAUNCHES -= 1          # D pre-pass + ONE backward kernel for resident items; longer sequences run the dK/dV and dQ passes
     check(lib.ub_attn_bwd(_p(qkv, BF16, "qkv"), _p(o, BF16, "o"), _p(d_o, BF16, "d_o"), _p(lse, F32, "lse"),
                           _p(d_ws, F32, "D_ws"), _p(dqkv, BF16, "dqkv"), _p(dbias, F32, "dbias"), n_seq, S, H, scale, _stream()), "ub_attn_bwd")
 
