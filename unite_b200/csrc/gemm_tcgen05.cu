@@ -30,7 +30,19 @@ namespace ub {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int EPI_BYTES = 8 * 2 * 4096;   // 8 epilogue warps x 2 staging slabs of 32 rows x 128 B
+// Staging slabs (32 rows x 128 B) per epilogue warp.  The epilogues that READ an operand through TMA (fp32 / fp16 residual,
+// GELU pre-activation) get three, so that the operand of slab n+2 is requested while slab n is processed: with two, the request
+// went out one slab (~0.4 us) ahead of its use against a TMA round trip of ~1 us, and K = 768 GEMMs were bound by that wait
+// (proj forward 27 us against 17 us for cuBLAS without any epilogue).  The third slab is paid for with one mainloop stage.
+#ifndef UB_GEMM_EPI_NBUF
+#define UB_GEMM_EPI_NBUF 3
+#endif
+template <int BN, int EPI, int NCTA>
+struct GemmCfg {
+  static constexpr int NBUF = (EPI != 0 && !(BN == 256 && NCTA == 1)) ? UB_GEMM_EPI_NBUF : 2;
+  static constexpr int EPI_BYTES = 8 * NBUF * 4096;      // 8 epilogue warps x NBUF staging slabs
+  static constexpr int stages(int requested) { return NBUF == 3 && requested > 4 ? 4 : requested; }
+};
 
 struct GemmParams {
   int M, N, K;
@@ -72,6 +84,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t IDESC = p.ab_f16 ? (IDESC_BF16 & ~FMT_BF16) : IDESC_BF16;
   constexpr int CW = OUT32 ? 32 : 64;        // columns per epilogue slab
   constexpr int SLABS = (BN / 2) / CW;       // slabs per warp per tile
+  constexpr int NBUF = GemmCfg<BN, EPI, NCTA>::NBUF;
+  constexpr int EPI_BYTES = GemmCfg<BN, EPI, NCTA>::EPI_BYTES;
   static_assert(EPI != 1 || OUT32, "residual epilogue writes fp32");
   static_assert(EPI != 2 || !OUT32, "DGELU epilogue writes bf16");
   static_assert(EPI != 3 || !OUT32, "the fp16-residual epilogue writes fp16");
@@ -82,14 +96,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const bool leader = pr == 0;
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* epi_s = smem + STAGES * STAGE_BYTES;                       // [8 warps][2][4096], 1024-aligned
+  uint8_t* epi_s = smem + STAGES * STAGE_BYTES;                       // [8 warps][NBUF][4096], 1024-aligned
   float* bias_s = reinterpret_cast<float*>(epi_s + EPI_BYTES);         // [2][BN]
   uint64_t* full = reinterpret_cast<uint64_t*>(bias_s + 2 * BN);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* rbar = tempty + 2;                                         // [8 warps][2] residual / aux slab arrived
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 16);
+  uint64_t* rbar = tempty + 2;                                         // [8 warps][3] residual / aux slab arrived
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 24);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,7 +121,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 8 * CG);     // the leader's copy collects the epilogue warps of both CTAs
     }
-    for (int i = 0; i < 16; ++i) mbar_init(&rbar[i], 1);
+    for (int i = 0; i < 24; ++i) mbar_init(&rbar[i], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -241,9 +255,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int sp = warp & 3;            // TMEM sub-partition this warp may read
     const int half = we >> 2;           // which half of the BN columns
     const int etid = threadIdx.x - 64;  // 0..255
-    uint8_t* const slab0 = epi_s + we * 8192;          // two 4 KB staging slabs: slab0 + (b << 12)
+    uint8_t* const slab0 = epi_s + we * (NBUF * 4096);   // NBUF 4 KB staging slabs: slab0 + (b << 12)
     const uint32_t slab0_a = smem_u32(slab0);
-    uint64_t* rb = rbar + we * 2;
+    uint64_t* rb = rbar + we * 3;
     const uint32_t sw = (uint32_t)(lane & 7);      // 16-byte chunk XOR of this lane's row (128B swizzle)
     const uint32_t rowoff = (uint32_t)lane * 128u;
     int as = 0;
@@ -253,9 +267,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     auto slab_row = [&](int w) { return ((w / p.splits) / n_tiles) * (BM * NCTA) + (int)cta_rank * BM + sp * 32; };
     auto slab_col = [&](int w, int c) { return ((w / p.splits) % n_tiles) * BN + half * (BN / 2) + c * CW; };
     if (EPI != 0 && w_first < total_work && lane == 0) {
-      // residual / pre-activation slab of the very first (tile, slab) of this warp
+      // residual / pre-activation slabs of the first NBUF - 1 (tile, slab) pairs of this warp
       mbar_expect_tx(&rb[0], 4096);
       tma_load_2d(&tmR, &rb[0], slab0, slab_col(w_first, 0), slab_row(w_first));
+      if (NBUF == 3) {
+        int nw = w_first, nc = 1;
+        if (nc == SLABS) { nc = 0; nw += w_step; }
+        if (nw < total_work) {
+          mbar_expect_tx(&rb[1], 4096);
+          tma_load_2d(&tmR, &rb[1], slab0 + 4096, slab_col(nw, nc), slab_row(nw));
+        }
+      }
     }
     for (int w = w_first; w < total_work; w += w_step) {
       const int n0 = ((w / p.splits) % n_tiles) * BN;
@@ -286,7 +308,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t t_row = tmem_base + ((uint32_t)(sp * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
 #pragma unroll 1
       for (int c = 0; c < SLABS; ++c, ++cc) {
-        const int b = cc & 1;
+        const int b = NBUF == 3 ? (int)(cc % 3u) : (int)(cc & 1u);
         const int col0 = slab_col(w, c);
         // ---- staging-buffer hand-over with the TMA engine
         if (EPI == 0) {
@@ -296,18 +318,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           __syncwarp();
         } else {
-          // the store of the previous slab read buffer b^1: once done, prefetch the NEXT slab's operand into it
+          // the store of the previous slab read buffer (cc - 1) % NBUF: once done, the operand of the slab NBUF - 1 ahead is
+          // prefetched into it
           if (lane == 0) {
             tma_store_wait_read<0>();
-            int nw = w, nc = c + 1;
-            if (nc == SLABS) { nc = 0; nw = w + w_step; }
+            int nw = w, nc = c + (NBUF - 1);
+            while (nc >= SLABS) { nc -= SLABS; nw += w_step; }
             if (nw < total_work) {
-              mbar_expect_tx(&rb[b ^ 1], 4096);
-              tma_load_2d(&tmR, &rb[b ^ 1], slab0 + ((b ^ 1) << 12), slab_col(nw, nc), slab_row(nw));
+              const int nb = NBUF == 3 ? (int)((cc + 2u) % 3u) : (b ^ 1);
+              mbar_expect_tx(&rb[nb], 4096);
+              tma_load_2d(&tmR, &rb[nb], slab0 + (nb << 12), slab_col(nw, nc), slab_row(nw));
             }
           }
           __syncwarp();
-          mbar_wait(&rb[b], (cc >> 1) & 1);
+          mbar_wait(&rb[b], NBUF == 3 ? ((cc / 3u) & 1u) : ((cc >> 1) & 1u));
         }
         // ---- accumulators -> registers -> epilogue math -> staging slab (row per lane, 128 B per row)
 #pragma unroll
@@ -561,9 +585,11 @@ struct GemmMaps {
   CUtensorMap a, b, c, r, x;
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, bool OUT32, int NCTA>
+template <int BN, int STAGES_REQ, bool A_MN, bool B_MN, int EPI, bool OUT32, int NCTA>
 static int launch_gemm_epi(const GemmMaps& m, const GemmParams& p, int grid, cudaStream_t stream) {
-  constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / (NCTA >= 2 ? 2 : 1)) * BK * 2) + EPI_BYTES + 2 * BN * 4 + (2 * STAGES + 4 + 16) * 8 + 16;
+  constexpr int STAGES = GemmCfg<BN, EPI, NCTA>::stages(STAGES_REQ);
+  constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / (NCTA >= 2 ? 2 : 1)) * BK * 2) + GemmCfg<BN, EPI, NCTA>::EPI_BYTES + 2 * BN * 4 +
+                       (2 * STAGES + 4 + 24) * 8 + 16;
   static_assert(SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
   static bool configured = false;
   auto kern = gemm_kernel<BN, STAGES, A_MN, B_MN, EPI, OUT32, NCTA>;
@@ -596,7 +622,7 @@ static int max_clusters4() {
   static int cached = -1;
   if (cached >= 0) return cached;
   auto kern = gemm_kernel<256, 5, false, false, 0, false, 4>;
-  constexpr int SMEM = 5 * (BM * BK * 2 + 128 * BK * 2) + EPI_BYTES + 2 * 256 * 4 + (2 * 5 + 4 + 16) * 8 + 16;
+  constexpr int SMEM = 5 * (BM * BK * 2 + 128 * BK * 2) + GemmCfg<256, 0, 4>::EPI_BYTES + 2 * 256 * 4 + (2 * 5 + 4 + 24) * 8 + 16;
   int n = 0;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) == cudaSuccess) {
     cudaLaunchConfig_t q{};
