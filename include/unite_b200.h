@@ -69,6 +69,13 @@ typedef struct ub_gemm_epilogue {
   float ln_eps;
   float* colsum_out;    /* DGELU epilogue only: += column sums over the M rows of the values written to C — the bias gradient of
                          * the Linear whose pre-activation is aux_in (saves the separate pass over C)                          */
+  /* Grouped GEMM: several independent products of the same shape in ONE launch (the K alignment decoders of
+   * modeling_adaptation.py:203-213, 322-325: y_k = z_k W_k^T + b_k, their dgrad and wgrad) — one wave-quantisation loss and one
+   * launch instead of K.  C is the groups' outputs stacked along M (M = total rows, group_rows rows each, a multiple of 256);
+   * the tile whose first row is m0 belongs to group g = m0 / group_rows and reads its operands at
+   *   A: k + g * group_a_k, m - g * group_a_m        B: k + g * group_b_k, n + g * group_b_n        bias[n + g * group_bias]
+   * (offsets in elements of the respective dimension; K is the per-group contraction length).  All 0 = ordinary GEMM.          */
+  int32_t group_rows, group_a_k, group_a_m, group_b_k, group_b_n, group_bias;
 } ub_gemm_epilogue;
 
 /* a_mn_major / b_mn_major = 1: the operand is stored transposed, i.e. A is [K, lda>=M] / B is [K, ldb>=N]

@@ -137,6 +137,24 @@ def test_full_vitb16_stage1_at_bench_batch_32_against_oracle():
     l_rel = abs(loss.item() - ref["loss"].item()) / abs(ref["loss"].item())
     print(f"B=32: targets max {t_err.max():.2e}, outputs max {o_err.max():.2e}, loss {loss.item():.6f} vs {ref['loss'].item():.6f} ({l_rel:.1e})")
     assert t_err.max() < FEAT_TOL and o_err.max() < FEAT_TOL and l_rel < LOSS_TOL
+    # grouped decoder GEMMs (one launch for the K heads: forward, dgrad, wgrad — active at these shapes) against the K separate
+    # launches on the same inputs: identical math, different fp32 accumulation order
+    assert eng.core._grouped(B * 320), "the grouped decoder path is not active at the benchmarked shapes"
+    arena = eng.core.arena
+    names = [f"clip_decoder.{k}.head.weight" for k in range(6)] + ["clip_decoder.3.head.bias", "encoder.blocks.11.mlp.fc2.weight",
+                                                                    "encoder.blocks.6.attn.qkv.weight", "encoder.blocks.0.mlp.fc1.weight"]
+    g_grouped = {n: arena.g32(n).clone() for n in names}
+    out_grouped = eng.last["outputs"].clone()
+    eng.core._group_dec = False
+    eng.core._dec_ws.clear()
+    eng.optimizer.zero_grad()
+    eng.forward_backward(videos.cuda(), q.cuda(), attn_override=ref["attn"].cuda().contiguous())
+    torch.cuda.synchronize()
+    assert rel_l2(out_grouped, eng.last["outputs"]) < 1e-6
+    for n in names:
+        assert rel_l2(g_grouped[n], arena.g32(n)) < 2e-4, (n, rel_l2(g_grouped[n], arena.g32(n)))
+    eng.core._group_dec = True
+    eng.core._dec_ws.clear()
     # the mask the engine derives from ITS OWN attention differs from the oracle's only where attn/q ties are within fp noise
     eng.forward_backward(videos.cuda(), q.cuda())
     torch.cuda.synchronize()

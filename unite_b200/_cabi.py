@@ -36,6 +36,12 @@ class GemmEpilogue(C.Structure):
         ("ln_inv_d", C.c_float),
         ("ln_eps", C.c_float),
         ("colsum_out", C.c_void_p),
+        ("group_rows", C.c_int32),
+        ("group_a_k", C.c_int32),
+        ("group_a_m", C.c_int32),
+        ("group_b_k", C.c_int32),
+        ("group_b_n", C.c_int32),
+        ("group_bias", C.c_int32),
     ]
 
 

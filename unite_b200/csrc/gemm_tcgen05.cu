@@ -59,6 +59,11 @@ struct GemmParams {
   float ln_inv_d, ln_eps;
   float* stats_out;         // EPI 3: row (sum, sumsq) of the fp16 output
   float* colsum_out;        // EPI 2: += column sums of the values written to C (the bias gradient of the Linear that produced aux)
+  // grouped GEMM (ub_gemm_epilogue.group_*): work item with first C row m0 belongs to group g = m0 / group_rows
+  int group_rows;           // 0 = ungrouped
+  int a_k_off, a_m_off;     // A coordinates: k += g * a_k_off, m -= g * a_m_off
+  int b_k_off, b_n_off;     // B coordinates: k += g * b_k_off, n += g * b_n_off
+  int bias_off;             // bias index += g * bias_off
 };
 
 // EPI : 0 = bias / activation (/ pre-activation copy), 1 = + fp32 residual (fp32 out), 2 = DGELU: * gelu'(aux) (bf16 out),
@@ -152,8 +157,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int w = w_first; w < total_work; w += w_step) {
       const int ks = w % p.splits;
       const int tile = w / p.splits;
-      const int m0 = (tile / n_tiles) * (BM * NCTA) + (int)cta_rank * BM;      // this CTA's rows of A
-      const int n0 = (tile % n_tiles) * BN + (int)pr * BN_L;                   // this CTA's rows of B
+      const int grp = p.group_rows ? ((tile / n_tiles) * (BM * NCTA)) / p.group_rows : 0;
+      const int m0 = (tile / n_tiles) * (BM * NCTA) + (int)cta_rank * BM - grp * p.a_m_off;      // this CTA's rows of A
+      const int n0 = (tile % n_tiles) * BN + (int)pr * BN_L + grp * p.b_n_off;                   // this CTA's rows of B
+      const int ka = grp * p.a_k_off, kbo = grp * p.b_k_off;                                     // K offsets of the group
       const int kb0 = ks * p.kb_per_split;
       const int kb1 = min(total_kb, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -167,34 +174,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (leader) mbar_expect_tx(&full[stage], STAGE_BYTES * 2);
             if (A_MN) {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg2(&tmA, lbar, sA + j * 8192, m0 + j * 64, kb * BK);
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg2(&tmA, lbar, sA + j * 8192, m0 + j * 64, kb * BK + ka);
             } else {
-              tma_load_2d_cg2(&tmA, lbar, sA, kb * BK, m0);
+              tma_load_2d_cg2(&tmA, lbar, sA, kb * BK + ka, m0);
             }
             if (NCTA == 4) {
               // this CTA's quarter of the B tile (64 rows / one 64-wide MN chunk = 8 KB) lands in both pairs
               const uint16_t mask = (uint16_t)((1u << pr) | (1u << (CG + pr)));
-              if (B_MN) tma_load_2d_cg2_mc(&tmB, lbar, sB + pp * 8192, n0 + (int)pp * 64, kb * BK, mask);
-              else tma_load_2d_cg2_mc(&tmB, lbar, sB + pp * 8192, kb * BK, n0 + (int)pp * 64, mask);
+              if (B_MN) tma_load_2d_cg2_mc(&tmB, lbar, sB + pp * 8192, n0 + (int)pp * 64, kb * BK + kbo, mask);
+              else tma_load_2d_cg2_mc(&tmB, lbar, sB + pp * 8192, kb * BK + kbo, n0 + (int)pp * 64, mask);
             } else if (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BN_L / 64; ++j) tma_load_2d_cg2(&tmB, lbar, sB + j * 8192, n0 + j * 64, kb * BK);
+              for (int j = 0; j < BN_L / 64; ++j) tma_load_2d_cg2(&tmB, lbar, sB + j * 8192, n0 + j * 64, kb * BK + kbo);
             } else {
-              tma_load_2d_cg2(&tmB, lbar, sB, kb * BK, n0);
+              tma_load_2d_cg2(&tmB, lbar, sB, kb * BK + kbo, n0);
             }
           } else {
             mbar_expect_tx(&full[stage], STAGE_BYTES);
             if (A_MN) {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d(&tmA, &full[stage], sA + j * 8192, m0 + j * 64, kb * BK);
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(&tmA, &full[stage], sA + j * 8192, m0 + j * 64, kb * BK + ka);
             } else {
-              tma_load_2d(&tmA, &full[stage], sA, kb * BK, m0);
+              tma_load_2d(&tmA, &full[stage], sA, kb * BK + ka, m0);
             }
             if (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BN_L / 64; ++j) tma_load_2d(&tmB, &full[stage], sB + j * 8192, n0 + j * 64, kb * BK);
+              for (int j = 0; j < BN_L / 64; ++j) tma_load_2d(&tmB, &full[stage], sB + j * 8192, n0 + j * 64, kb * BK + kbo);
             } else {
-              tma_load_2d(&tmB, &full[stage], sB, kb * BK, n0);
+              tma_load_2d(&tmB, &full[stage], sB, kb * BK + kbo, n0);
             }
           }
         }
@@ -284,7 +291,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int row0 = slab_row(w);
       float* bias_tile = bias_s + as * BN;
       if (p.bias != nullptr) {
-        if (etid < BN) bias_tile[etid] = (n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.0f;
+        const int goff = p.group_rows ? ((((w / p.splits) / n_tiles) * (BM * NCTA)) / p.group_rows) * p.bias_off : 0;
+        if (etid < BN) bias_tile[etid] = (n0 + etid < p.N) ? __ldg(p.bias + goff + n0 + etid) : 0.0f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       float rscale = 1.0f;
@@ -693,6 +701,16 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
              "gemm: residual cannot be combined with an activation / accumulate");
   UB_REQUIRE(ep.aux_out == nullptr || (ep.act == UB_ACT_GELU && !ep.out_fp32), "gemm: aux_out is the bf16 GELU pre-activation copy");
 
+  const int G = ep.group_rows > 0 ? (M + ep.group_rows - 1) / ep.group_rows : 1;      // groups of a grouped GEMM
+  UB_REQUIRE(ep.group_rows >= 0 && (ep.group_rows == 0 || (ep.group_rows % 256 == 0 && M % ep.group_rows == 0)),
+             "gemm: group_rows=%d must be a multiple of 256 that divides M=%d", ep.group_rows, M);
+  UB_REQUIRE(ep.group_rows > 0 || (ep.group_a_k | ep.group_a_m | ep.group_b_k | ep.group_b_n | ep.group_bias) == 0,
+             "gemm: group offsets need group_rows");
+  UB_REQUIRE(ep.group_rows == 0 || (ep.residual == nullptr && ep.aux_in == nullptr && ep.aux_out == nullptr && ep.row_scale == nullptr &&
+                                    ep.ln_stats == nullptr && ep.stats_out == nullptr && ep.colsum_out == nullptr),
+             "gemm: a grouped GEMM supports the bias / accumulate epilogues only");
+  UB_REQUIRE(ep.group_rows == 0 || (ep.group_a_k % BK == 0 && ep.group_b_k % BK == 0 && K % BK == 0),
+             "gemm: grouped K offsets and K must be multiples of %d", BK);
   const int total_kb = (K + BK - 1) / BK;
   if (split_k > total_kb) split_k = total_kb;
   int kb_per_split = (total_kb + split_k - 1) / split_k;
@@ -748,15 +766,18 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   const bool out32 = ep.out_fp32 != 0;
   GemmMaps m;
   memset(&m, 0, sizeof(m));
+  // operand extents (a grouped GEMM addresses all groups through one map: the group offsets widen the respective dimension)
+  const int64_t a_k_ext = (int64_t)K + (int64_t)(G - 1) * ep.group_a_k, a_m_ext = ep.group_a_m > 0 ? ep.group_a_m : M;
+  const int64_t b_k_ext = (int64_t)K + (int64_t)(G - 1) * ep.group_b_k, b_n_ext = (int64_t)N + (int64_t)(G - 1) * ep.group_b_n;
   if (a_mn_major) {
-    if (make_tmap_2d(&m.a, A, K, M, lda, 64, 64, 2)) return 1;
+    if (make_tmap_2d(&m.a, A, a_k_ext, a_m_ext, lda, 64, 64, 2)) return 1;
   } else {
-    if (make_tmap_2d(&m.a, A, M, K, lda, BK, BM, 2)) return 1;
+    if (make_tmap_2d(&m.a, A, a_m_ext, a_k_ext, lda, BK, BM, 2)) return 1;
   }
   if (b_mn_major) {
-    if (make_tmap_2d(&m.b, B, K, N, ldb, 64, 64, 2)) return 1;
+    if (make_tmap_2d(&m.b, B, b_k_ext, b_n_ext, ldb, 64, 64, 2)) return 1;
   } else {
-    if (make_tmap_2d(&m.b, B, N, K, ldb, BK, bn / ncta, 2)) return 1;
+    if (make_tmap_2d(&m.b, B, b_n_ext, b_k_ext, ldb, BK, bn / ncta, 2)) return 1;
   }
   if (make_tmap_2d(&m.c, C, M, N, ldc, out32 ? 32 : 64, 32, out32 ? 4 : 2)) return 1;
   m.r = m.c;
@@ -775,6 +796,8 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   p.ln_stats = ep.ln_stats; p.ln_c = ep.ln_c; p.ln_inv_d = ep.ln_inv_d; p.ln_eps = ep.ln_eps;
   p.stats_out = ep.stats_out;
   p.colsum_out = ep.colsum_out;
+  p.group_rows = ep.group_rows; p.a_k_off = ep.group_a_k; p.a_m_off = ep.group_a_m;
+  p.b_k_off = ep.group_b_k; p.b_n_off = ep.group_b_n; p.bias_off = ep.group_bias;
   const long total_work = (long)((M + BM * ncta - 1) / (BM * ncta)) * ((N + bn - 1) / bn) * split_k;
   int units = ncta == 4 ? units4 : sms / ncta;
   if (ep.max_ctas > 0 && ep.max_ctas / ncta >= 1 && ep.max_ctas / ncta < units) units = ep.max_ctas / ncta;

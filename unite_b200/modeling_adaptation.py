@@ -211,6 +211,18 @@ class AdaptationCore:
         self.clip_pos = model.clip_pos_embed[0].to(dev).contiguous()
         self._shadow_version = None
         self._dec_ws: Dict = {}
+        # The K decoder heads as ONE grouped GEMM (forward, dgrad, wgrad): possible when their weights sit back to back in the
+        # arena (they do: the decay segment starts with clip_decoder.{k}.head.weight in order) and their biases at a fixed stride
+        K = len(self.taps)
+        offs = [self.arena.offsets[f"clip_decoder.{k}.head.weight"][0] for k in range(K)]
+        boffs = [self.arena.offsets[f"clip_decoder.{k}.head.bias"][0] for k in range(K)]
+        wsz = self.C * self.D
+        import os
+        self._group_dec = (os.environ.get("UB_GROUP_DECODERS", "1") == "1" and K > 1 and self.C % 256 == 0
+                           and all(offs[k + 1] - offs[k] == wsz for k in range(K - 1))
+                           and len({boffs[k + 1] - boffs[k] for k in range(K - 1)}) == 1 and boffs[1] > boffs[0])
+        self._dec_w_off, self._dec_b_off = offs[0], boffs[0]
+        self._dec_b_stride = (boffs[1] - boffs[0]) if K > 1 else 0
         import os
         self.drop_path = DropPathSource(enc.drop_path_rates, dev, seed=int(os.environ.get("UB_DROP_PATH_SEED", "0")))
 
@@ -231,10 +243,14 @@ class AdaptationCore:
             d = dict(z=torch.empty(K if save else 1, M, self.D, device=dev, dtype=BF16),
                      y=torch.empty(K if save else 1, M, self.C, device=dev, dtype=F32))
             if save:
-                d["dy"] = torch.empty(M, self.C, device=dev, dtype=BF16)
+                d["dy"] = torch.empty(K if self._grouped(M) else 1, M, self.C, device=dev, dtype=BF16)
                 d["dz"] = torch.empty(K, M, self.D, device=dev, dtype=BF16)
             self._dec_ws[key] = d
         return self._dec_ws[key]
+
+    def _grouped(self, M):
+        """The decoder heads run as one grouped GEMM when every group's rows are whole 256-row tiles."""
+        return self._group_dec and M % 256 == 0
 
     def run_forward(self, x, vis_idx, patches, dp, clip_only, save, targets=None, loss_acc=None, want_clip=True, abs_rows=None,
                     loss_clips=None):
@@ -269,6 +285,12 @@ class AdaptationCore:
         loss_rows = None if loss_clips is None else (loss_clips[0] * Nv, loss_clips[1] * Nv)
         loss_scale = 1.0 / (K * (M if loss_rows is None else max(1, loss_rows[1] - loss_rows[0])))
 
+        grouped = save and want_clip and self._grouped(M)
+
+        def dec_tail(k, y):
+            ops.dec_tail_fwd(y, a.p32(f"clip_decoder.{k}.norm.weight"), a.p32(f"clip_decoder.{k}.norm.bias"), self.eps, out[k],
+                             None if targets is None else targets[k].reshape(M, self.C), loss_acc, loss_scale, loss_rows)
+
         def after_layer(l, x_l):
             if l not in tap_of or not want_clip:
                 return
@@ -276,11 +298,21 @@ class AdaptationCore:
             z = dws["z"][k if save else 0]
             y = dws["y"][k if save else 0]
             ops.layernorm_fwd(x_l, enc_w, enc_b, self.eps, z, post_add=self.clip_pos, post_idx=vis_flat)
+            if grouped:
+                return                                   # the K head GEMMs run as one grouped launch after the trunk
             ops.gemm(z, a.b16(f"clip_decoder.{k}.head.weight"), y, bias=a.p32(f"clip_decoder.{k}.head.bias"))
-            ops.dec_tail_fwd(y, a.p32(f"clip_decoder.{k}.norm.weight"), a.p32(f"clip_decoder.{k}.norm.bias"), self.eps, out[k],
-                             None if targets is None else targets[k].reshape(M, self.C), loss_acc, loss_scale, loss_rows)
+            dec_tail(k, y)
 
         ws = self.trunk.forward(p_vis, pos_vis, B, Nv, n_layers, save, dp, after_layer=after_layer)
+        if grouped:
+            # y_k = z_k W_k^T + b_k for all K decoders (modeling_adaptation.py:203-213, 322-325) in one launch: 480 pair tiles
+            # instead of 6 launches of 80 (1.08 waves each on 74 CTA pairs)
+            W = a.w16[self._dec_w_off:self._dec_w_off + K * self.C * self.D].view(K * self.C, self.D)
+            bias = a.params[self._dec_b_off:self._dec_b_off + (K - 1) * self._dec_b_stride + self.C]
+            ops.gemm(dws["z"].view(K * M, self.D), W, dws["y"].view(K * M, self.C), bias=bias,
+                     group=dict(rows=M, K=self.D, b_n=self.C, bias=self._dec_b_stride))
+            for k in range(K):
+                dec_tail(k, dws["y"][k])
         x_vis = None
         if not clip_only:
             x_vis = torch.empty(M, self.D, device=dev, dtype=F32)
@@ -309,13 +341,27 @@ class AdaptationCore:
                 go = go.contiguous().float()
             go_rows = state.get("loss_rows") if targets is not None else None
             go_scale = -2.0 / (K * (M if go_rows is None else max(1, go_rows[1] - go_rows[0]))) if targets is not None else 1.0
+            grouped = dws["dy"].shape[0] == K and K > 1
             for k in range(K):
+                dy = dws["dy"][k if grouped else 0]
                 ops.dec_tail_bwd(dws["y"][k], a.p32(f"clip_decoder.{k}.norm.weight"), a.p32(f"clip_decoder.{k}.norm.bias"), self.eps,
-                                 go[k], go_scale, dws["dy"], a.g32(f"clip_decoder.{k}.norm.weight"), a.g32(f"clip_decoder.{k}.norm.bias"),
+                                 go[k], go_scale, dy, a.g32(f"clip_decoder.{k}.norm.weight"), a.g32(f"clip_decoder.{k}.norm.bias"),
                                  go_rows)
-                self.trunk._wgrad(dws["dy"], dws["z"][k], a.g32(f"clip_decoder.{k}.head.weight"))
-                ops.colsum_bf16(dws["dy"], a.g32(f"clip_decoder.{k}.head.bias"))
-                ops.gemm(dws["dy"], a.b16(f"clip_decoder.{k}.head.weight"), dws["dz"][k], b_t=True)
+                ops.colsum_bf16(dy, a.g32(f"clip_decoder.{k}.head.bias"))
+                if not grouped:
+                    self.trunk._wgrad(dy, dws["z"][k], a.g32(f"clip_decoder.{k}.head.weight"))
+                    ops.gemm(dy, a.b16(f"clip_decoder.{k}.head.weight"), dws["dz"][k], b_t=True)
+            if grouped:
+                # the K weight gradients dW_k += dy_k^T z_k and the K input gradients dz_k = dy_k W_k as two grouped launches
+                C_, D_ = self.C, self.D
+                n_w = K * C_ * D_
+                gW = a.grads[self._dec_w_off:self._dec_w_off + n_w].view(K * C_, D_)
+                W = a.w16[self._dec_w_off:self._dec_w_off + n_w].view(K * C_, D_)
+                dy_all = dws["dy"].view(K * M, C_)
+                from .vit_core import _splits_for
+                ops.gemm(dy_all, dws["z"].view(K * M, D_), gW, a_t=True, b_t=True, accumulate=True,
+                         split_k=_splits_for(K * C_, D_, self.trunk.sms), group=dict(rows=C_, K=M, a_k=M, a_m=C_, b_k=M))
+                ops.gemm(dy_all, W, dws["dz"].view(K * M, D_), b_t=True, group=dict(rows=M, K=C_, b_k=C_))
         taps = {}
         N = state["Nv"]
 

@@ -39,7 +39,7 @@ def _instrument(name, n_kernels):
             info = None
             if name == "gemm":
                 out = a[2]
-                K = a[0].shape[0] if k.get("a_t") else a[0].shape[1]
+                K = k["group"]["K"] if k.get("group") else (a[0].shape[0] if k.get("a_t") else a[0].shape[1])
                 info = (out.shape[0], out.shape[1], K, bool(k.get("a_t")), bool(k.get("b_t")), out.dtype == F32)
             PROFILE.append((name, info, e0, e1))
             return r
@@ -70,11 +70,13 @@ def _p2d(t: torch.Tensor, dtype, what):
 @_instrument("gemm", 1)
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=False, bias=None, residual=None,
          row_scale=None, rows_per_scale=0, act=UB_ACT_NONE, aux_in=None, aux_out=None, accumulate=False, split_k=1, tile_ctas=0,
-         max_ctas=0, ln_stats=None, ln_c=None, ln_eps=0.0, stats_out=None, colsum_out=None):
+         max_ctas=0, ln_stats=None, ln_c=None, ln_eps=0.0, stats_out=None, colsum_out=None, group=None):
     """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).  a_t / b_t: the operand is stored transposed ([K,M] / [K,N]).
     A and B are both bf16 or both fp16.  ln_stats / ln_c: LayerNorm of A's rows folded into the epilogue (see the header);
     stats_out: row (sum, sumsq) of an fp16-residual output, accumulated.  colsum_out (DGELU epilogue): fp32 [N], += column sums
-    of the output over its M rows (the bias gradient of the Linear whose pre-activation is aux_in)."""
+    of the output over its M rows (the bias gradient of the Linear whose pre-activation is aux_in).
+    group: dict(rows=, K=, a_k=0, a_m=0, b_k=0, b_n=0, bias=0) — a grouped GEMM (see ub_gemm_epilogue.group_*): `out` stacks the
+    groups' outputs along M, K is the per-group contraction length and the operands are addressed with the group offsets."""
     ab = F16 if a.dtype == F16 else BF16
     pa, lda = _p2d(a, ab, "gemm A")
     pb, ldb = _p2d(b, ab, "gemm B")
@@ -84,14 +86,23 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=
         raise _cabi.UBError("gemm out: fp16 output is only produced by the fp16-residual epilogue")
     pc, ldc = _p2d(out, out.dtype, "gemm C")
     M, N = out.shape
-    K = a.shape[0] if a_t else a.shape[1]
-    am, bn = (a.shape[1] if a_t else a.shape[0]), (b.shape[1] if b_t else b.shape[0])
-    bk = b.shape[0] if b_t else b.shape[1]
-    if am != M or bn != N or bk != K:
-        raise _cabi.UBError(f"gemm: shape mismatch A{tuple(a.shape)} a_t={a_t} B{tuple(b.shape)} b_t={b_t} C{tuple(out.shape)}")
     ep = GemmEpilogue()
+    if group is None:
+        K = a.shape[0] if a_t else a.shape[1]
+        am, bn = (a.shape[1] if a_t else a.shape[0]), (b.shape[1] if b_t else b.shape[0])
+        bk = b.shape[0] if b_t else b.shape[1]
+        if am != M or bn != N or bk != K:
+            raise _cabi.UBError(f"gemm: shape mismatch A{tuple(a.shape)} a_t={a_t} B{tuple(b.shape)} b_t={b_t} C{tuple(out.shape)}")
+    else:
+        K, G = int(group["K"]), M // int(group["rows"])
+        ep.group_rows, ep.group_a_k, ep.group_a_m = int(group["rows"]), int(group.get("a_k", 0)), int(group.get("a_m", 0))
+        ep.group_b_k, ep.group_b_n, ep.group_bias = int(group.get("b_k", 0)), int(group.get("b_n", 0)), int(group.get("bias", 0))
+        a_k_ext, a_m_ext = K + (G - 1) * ep.group_a_k, (ep.group_a_m or M)
+        b_k_ext, b_n_ext = K + (G - 1) * ep.group_b_k, N + (G - 1) * ep.group_b_n
+        if tuple(a.shape) != ((a_k_ext, a_m_ext) if a_t else (a_m_ext, a_k_ext)) or tuple(b.shape) != ((b_k_ext, b_n_ext) if b_t else (b_n_ext, b_k_ext)):
+            raise _cabi.UBError(f"grouped gemm: operand shapes A{tuple(a.shape)} B{tuple(b.shape)} do not match the group layout {group} for C{tuple(out.shape)}")
     if bias is not None:
-        if bias.numel() != N:
+        if group is None and bias.numel() != N:
             raise _cabi.UBError("gemm bias: wrong length")
         ep.bias = _p(bias, F32, "gemm bias")
     if residual is not None:
