@@ -24,7 +24,7 @@ def run(setting, steps, warmup, gpus, port):
     cmd = [sys.executable]
     if gpus > 1:
         cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={gpus}", "--master-addr", "127.0.0.1", "--master-port", str(port)]
-    cmd += [os.path.join(ROOT, "bench.py"), "--gpus", str(gpus), "--steps", str(steps), "--warmup", str(warmup), "--no-cpu-baseline"]
+    cmd += [os.path.join(ROOT, "bench.py"), "--gpus", str(gpus), "--steps", str(steps), "--warmup", str(warmup), "--no-cpu-baseline", "--no-eager-baseline"]
     r = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
     lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
     if r.returncode != 0 or not lines:
