@@ -30,12 +30,13 @@ namespace ub {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-// Staging slabs (32 rows x 128 B) per epilogue warp.  The epilogues that READ an operand through TMA (fp32 / fp16 residual,
-// GELU pre-activation) get three, so that the operand of slab n+2 is requested while slab n is processed: with two, the request
-// went out one slab (~0.4 us) ahead of its use against a TMA round trip of ~1 us, and K = 768 GEMMs were bound by that wait
-// (proj forward 27 us against 17 us for cuBLAS without any epilogue).  The third slab is paid for with one mainloop stage.
+// Staging slabs (32 rows x 128 B) per epilogue warp: two.  -DUB_GEMM_EPI_NBUF=3 gives the epilogues that READ an operand through
+// TMA (fp32 / fp16 residual, GELU pre-activation) a third one, so that the operand of slab n+2 is requested while slab n is
+// processed (with two, the request goes out one slab, ~0.4 us, ahead of its use against a TMA round trip of ~1 us) — paid for with
+// one mainloop stage (4 instead of 5).  Measured on B200, A/B/A/B/A/B over whole steps: 17.998 ms (three slabs) vs 17.918 ms (two):
+// what the K = 768 residual GEMMs gain, the K = 3072 ones lose with the shallower ring.  So the default stays at two.
 #ifndef UB_GEMM_EPI_NBUF
-#define UB_GEMM_EPI_NBUF 3
+#define UB_GEMM_EPI_NBUF 2
 #endif
 template <int BN, int EPI, int NCTA>
 struct GemmCfg {
