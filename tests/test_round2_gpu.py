@@ -152,9 +152,9 @@ def test_full_vitb16_stage1_at_bench_batch_32_against_oracle():
     torch.cuda.synchronize()
     assert rel_l2(out_grouped, eng.last["outputs"]) < 1e-6
     for n in names:
-        # the decoders' own gradients see one summation-order change; the trunk's also carry the run-to-run order of the fp32
-        # red.adds of 12 layers of split-K weight gradients
-        tol = 2e-5 if n.startswith("clip_decoder") else 1e-3
+        # the decoders' own gradients see a different split-K factor (fp32 partial sums over 10 240 tokens with cancellation:
+        # ~1e-4 relative); the trunk's also carry the run-to-run order of the fp32 red.adds of 12 layers of weight gradients
+        tol = 3e-4 if n.startswith("clip_decoder") else 1e-3
         assert rel_l2(g_grouped[n], arena.g32(n)) < tol, (n, rel_l2(g_grouped[n], arena.g32(n)))
     eng.core._group_dec = True
     eng.core._dec_ws.clear()
