@@ -84,6 +84,18 @@ UB_API int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* 
                  void* C, int64_t ldc, int M, int N, int K, const ub_gemm_epilogue* ep, int split_k,
                  void* stream);
 
+/* Several weight gradients over the same tokens in one launch — the four Linear layers of a transformer block
+ * (modeling_finetune.py:56-119 under autograd: qkv, proj, fc1, fc2):  C_i[M_i, N_i] (fp32) += A_i^T B_i  with A_i = the bf16 output
+ * gradient stored [K tokens, lda >= M_i] and B_i = the bf16 layer input stored [K tokens, ldb >= N_i]; up to 4 problems, any M_i /
+ * N_i (multiples of 8), split_k ways along the tokens (fp32 reduce-add into C_i, which must hold the running gradient). */
+typedef struct ub_gemm_problem {
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  float* C; int64_t ldc;
+  int32_t M, N;
+} ub_gemm_problem;
+UB_API int ub_gemm_wgrad_multi(const ub_gemm_problem* problems, int n_problems, int K, int split_k, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fused multi-head self-attention, head_dim 64 (flash-style: the S x S scores never reach HBM).
  *   qkv bf16 [n_seq*S, 3*H*64] (per row q|k|v, H heads x 64), o bf16 [n_seq*S, H*64], lse fp32 [n_seq,H,S].

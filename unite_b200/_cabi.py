@@ -45,6 +45,11 @@ class GemmEpilogue(C.Structure):
     ]
 
 
+class GemmProblem(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("B", C.c_void_p), ("ldb", C.c_int64), ("C", C.c_void_p), ("ldc", C.c_int64),
+                ("M", C.c_int32), ("N", C.c_int32)]
+
+
 def _load():
     if not os.path.exists(_LIB_PATH):
         raise ImportError(
@@ -65,6 +70,7 @@ SIGNATURES = {
     "ub_set_sm_limit": (C.c_int, [_I]),
     "ub_gemm_cluster4_capacity": (C.c_int, []),
     "ub_gemm_bf16": (C.c_int, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, C.POINTER(GemmEpilogue), _I, _P]),
+    "ub_gemm_wgrad_multi": (C.c_int, [C.POINTER(GemmProblem), _I, _I, _I, _P]),
     "ub_attn_fwd": (C.c_int, [_P, _P, _P, _I, _I, _I, _F, _P]),
     "ub_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "ub_cls_attn": (C.c_int, [_P, _P, _I, _I, _I, _F, _P]),

@@ -65,6 +65,16 @@ struct GemmParams {
   int a_k_off, a_m_off;     // A coordinates: k += g * a_k_off, m -= g * a_m_off
   int b_k_off, b_n_off;     // B coordinates: k += g * b_k_off, n += g * b_n_off
   int bias_off;             // bias index += g * bias_off
+  // multi-problem launch (ub_gemm_wgrad_multi): n_prob products of the same K and operand majors but different M x N and
+  // buffers; tile t belongs to problem i with tile_off[i] <= t < tile_off[i + 1], which has ntile_n[i] tiles along N
+  int n_prob;
+  int tile_off[5];
+  int ntile_n[4];
+};
+
+constexpr int GEMM_MAX_PROB = 4;
+struct GemmMultiMaps {
+  CUtensorMap a[GEMM_MAX_PROB], b[GEMM_MAX_PROB], c[GEMM_MAX_PROB];
 };
 
 // EPI : 0 = bias / activation (/ pre-activation copy), 1 = + fp32 residual (fp32 out), 2 = DGELU: * gelu'(aux) (bf16 out),
@@ -73,11 +83,9 @@ struct GemmParams {
 // NCTA: 1 = one CTA per 128 x BN tile; 2 = CTA pair per 256 x BN tile; 4 = cluster of two pairs on a 512 x BN tile that
 //       share B: each CTA fetches a quarter of the B tile and TMA-multicasts it to the CTA of the same rank in the other pair
 //       (the mainloop is bound by L2 -> SM bytes: 24 KB instead of 32 KB per CTA and k-block)
-template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, bool OUT32, int NCTA>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-            const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, bool OUT32, int NCTA, bool MULTI>
+UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmR,
+                         const CUtensorMap& tmX, const GemmMultiMaps* mm, const GemmParams& p) {
   constexpr int CG = NCTA >= 2 ? 2 : 1;      // CTAs per MMA (tcgen05 cta_group)
   constexpr int NP = NCTA / CG;              // CTA pairs per cluster
   constexpr int BN_L = BN / CG;              // rows of B resident in this CTA
@@ -148,7 +156,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int m_tiles = (p.M + BM * NCTA - 1) / (BM * NCTA);
   const int n_tiles = (p.N + BN - 1) / BN;
   const int total_kb = (p.K + BK - 1) / BK;
-  const int total_work = m_tiles * n_tiles * p.splits;
+  const int total_work = (MULTI ? p.tile_off[p.n_prob] : m_tiles * n_tiles) * p.splits;
+  // (problem, tile row, tile column) of tile t: one problem unless MULTI
+  auto decode = [&](int t, int& pi, int& tm, int& tn) {
+    if (MULTI) {
+      pi = 0;
+#pragma unroll
+      for (int i = 1; i < GEMM_MAX_PROB; ++i) pi += (i < p.n_prob && t >= p.tile_off[i]) ? 1 : 0;
+      const int lt = t - p.tile_off[pi], ntn = p.ntile_n[pi];
+      tm = lt / ntn;
+      tn = lt - tm * ntn;
+    } else {
+      pi = 0;
+      tm = t / n_tiles;
+      tn = t - tm * n_tiles;
+    }
+  };
   const int w_first = blockIdx.x / NCTA, w_step = gridDim.x / NCTA;   // both CTAs of a pair walk the same work items
 
   if (warp == 0) {
@@ -158,9 +181,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int w = w_first; w < total_work; w += w_step) {
       const int ks = w % p.splits;
       const int tile = w / p.splits;
-      const int grp = p.group_rows ? ((tile / n_tiles) * (BM * NCTA)) / p.group_rows : 0;
-      const int m0 = (tile / n_tiles) * (BM * NCTA) + (int)cta_rank * BM - grp * p.a_m_off;      // this CTA's rows of A
-      const int n0 = (tile % n_tiles) * BN + (int)pr * BN_L + grp * p.b_n_off;                   // this CTA's rows of B
+      int pi, tm, tn;
+      decode(tile, pi, tm, tn);
+      const CUtensorMap* pA = MULTI ? &mm->a[pi] : &tmA;
+      const CUtensorMap* pB = MULTI ? &mm->b[pi] : &tmB;
+      const int grp = p.group_rows ? (tm * (BM * NCTA)) / p.group_rows : 0;
+      const int m0 = tm * (BM * NCTA) + (int)cta_rank * BM - grp * p.a_m_off;      // this CTA's rows of A
+      const int n0 = tn * BN + (int)pr * BN_L + grp * p.b_n_off;                   // this CTA's rows of B
       const int ka = grp * p.a_k_off, kbo = grp * p.b_k_off;                                     // K offsets of the group
       const int kb0 = ks * p.kb_per_split;
       const int kb1 = min(total_kb, kb0 + p.kb_per_split);
@@ -175,34 +202,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (leader) mbar_expect_tx(&full[stage], STAGE_BYTES * 2);
             if (A_MN) {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg2(&tmA, lbar, sA + j * 8192, m0 + j * 64, kb * BK + ka);
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg2(pA, lbar, sA + j * 8192, m0 + j * 64, kb * BK + ka);
             } else {
-              tma_load_2d_cg2(&tmA, lbar, sA, kb * BK + ka, m0);
+              tma_load_2d_cg2(pA, lbar, sA, kb * BK + ka, m0);
             }
             if (NCTA == 4) {
               // this CTA's quarter of the B tile (64 rows / one 64-wide MN chunk = 8 KB) lands in both pairs
               const uint16_t mask = (uint16_t)((1u << pr) | (1u << (CG + pr)));
-              if (B_MN) tma_load_2d_cg2_mc(&tmB, lbar, sB + pp * 8192, n0 + (int)pp * 64, kb * BK + kbo, mask);
-              else tma_load_2d_cg2_mc(&tmB, lbar, sB + pp * 8192, kb * BK + kbo, n0 + (int)pp * 64, mask);
+              if (B_MN) tma_load_2d_cg2_mc(pB, lbar, sB + pp * 8192, n0 + (int)pp * 64, kb * BK + kbo, mask);
+              else tma_load_2d_cg2_mc(pB, lbar, sB + pp * 8192, kb * BK + kbo, n0 + (int)pp * 64, mask);
             } else if (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BN_L / 64; ++j) tma_load_2d_cg2(&tmB, lbar, sB + j * 8192, n0 + j * 64, kb * BK + kbo);
+              for (int j = 0; j < BN_L / 64; ++j) tma_load_2d_cg2(pB, lbar, sB + j * 8192, n0 + j * 64, kb * BK + kbo);
             } else {
-              tma_load_2d_cg2(&tmB, lbar, sB, kb * BK + kbo, n0);
+              tma_load_2d_cg2(pB, lbar, sB, kb * BK + kbo, n0);
             }
           } else {
             mbar_expect_tx(&full[stage], STAGE_BYTES);
             if (A_MN) {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d(&tmA, &full[stage], sA + j * 8192, m0 + j * 64, kb * BK + ka);
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(pA, &full[stage], sA + j * 8192, m0 + j * 64, kb * BK + ka);
             } else {
-              tma_load_2d(&tmA, &full[stage], sA, kb * BK + ka, m0);
+              tma_load_2d(pA, &full[stage], sA, kb * BK + ka, m0);
             }
             if (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BN_L / 64; ++j) tma_load_2d(&tmB, &full[stage], sB + j * 8192, n0 + j * 64, kb * BK + kbo);
+              for (int j = 0; j < BN_L / 64; ++j) tma_load_2d(pB, &full[stage], sB + j * 8192, n0 + j * 64, kb * BK + kbo);
             } else {
-              tma_load_2d(&tmB, &full[stage], sB, kb * BK + kbo, n0);
+              tma_load_2d(pB, &full[stage], sB, kb * BK + kbo, n0);
             }
           }
         }
@@ -272,8 +299,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t aphase = 0;
     uint32_t cc = 0;                    // running slab counter of this warp: staging buffer = cc & 1
     // (row, col) of this warp's slab `c` of work item `w`
-    auto slab_row = [&](int w) { return ((w / p.splits) / n_tiles) * (BM * NCTA) + (int)cta_rank * BM + sp * 32; };
-    auto slab_col = [&](int w, int c) { return ((w / p.splits) % n_tiles) * BN + half * (BN / 2) + c * CW; };
+    auto slab_row = [&](int w) {
+      int pi, tm, tn;
+      decode(w / p.splits, pi, tm, tn);
+      return tm * (BM * NCTA) + (int)cta_rank * BM + sp * 32;
+    };
+    auto slab_col = [&](int w, int c) {
+      int pi, tm, tn;
+      decode(w / p.splits, pi, tm, tn);
+      return tn * BN + half * (BN / 2) + c * CW;
+    };
     if (EPI != 0 && w_first < total_work && lane == 0) {
       // residual / pre-activation slabs of the first NBUF - 1 (tile, slab) pairs of this warp
       mbar_expect_tx(&rb[0], 4096);
@@ -288,11 +323,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
     for (int w = w_first; w < total_work; w += w_step) {
-      const int n0 = ((w / p.splits) % n_tiles) * BN;
+      int w_pi, w_tm, w_tn;
+      decode(w / p.splits, w_pi, w_tm, w_tn);
+      const CUtensorMap* pC = MULTI ? &mm->c[w_pi] : &tmC;
+      const int n0 = w_tn * BN;
       const int row0 = slab_row(w);
       float* bias_tile = bias_s + as * BN;
       if (p.bias != nullptr) {
-        const int goff = p.group_rows ? ((((w / p.splits) / n_tiles) * (BM * NCTA)) / p.group_rows) * p.bias_off : 0;
+        const int goff = p.group_rows ? ((w_tm * (BM * NCTA)) / p.group_rows) * p.bias_off : 0;
         if (etid < BN) bias_tile[etid] = (n0 + etid < p.N) ? __ldg(p.bias + goff + n0 + etid) : 0.0f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
@@ -491,8 +529,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (p.accumulate) tma_reduce_add_2d(&tmC, slab0 + (b << 12), col0, row0);
-          else tma_store_2d(&tmC, slab0 + (b << 12), col0, row0);
+          if (p.accumulate) tma_reduce_add_2d(pC, slab0 + (b << 12), col0, row0);
+          else tma_store_2d(pC, slab0 + (b << 12), col0, row0);
           if (EPI == 0 && p.has_aux_out) tma_store_2d(&tmX, slab0 + ((b ^ 1) << 12), col0, row0);
           tma_store_commit();
         }
@@ -518,6 +556,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tc_fence_after();
     if (NCTA >= 2) tmem_dealloc_cg2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int EPI, bool OUT32, int NCTA>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+            const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
+  gemm_body<BN, STAGES, A_MN, B_MN, EPI, OUT32, NCTA, false>(tmA, tmB, tmC, tmR, tmX, nullptr, p);
+}
+
+// Several weight gradients of one backward block in ONE launch (TN, fp32 reduce-add, CTA pairs): dW_i += dY_i^T X_i for up to four
+// (dY_i, X_i, dW_i) of different widths over the same tokens.  The four launches it replaces each paid their own prologue /
+// pipeline fill / drain (~5 us) and their own wave quantisation on the 74 CTA pairs.
+template <int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_multi_kernel(const __grid_constant__ GemmMultiMaps mm, const GemmParams p) {
+  gemm_body<256, STAGES, true, true, 0, true, 2, true>(mm.a[0], mm.b[0], mm.c[0], mm.c[0], mm.c[0], &mm, p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -674,6 +729,66 @@ static int launch_gemm(const GemmMaps& m, const GemmParams& p, int epi, bool out
 }  // namespace ub
 
 extern "C" int ub_gemm_cluster4_capacity(void) { return ub::max_clusters4(); }
+
+extern "C" int ub_gemm_wgrad_multi(const ub_gemm_problem* pr, int n, int K, int split_k, void* stream) {
+  using namespace ub;
+  UB_REQUIRE(pr != nullptr && n >= 1 && n <= GEMM_MAX_PROB, "gemm_wgrad_multi: 1..%d problems expected (got %d)", GEMM_MAX_PROB, n);
+  UB_REQUIRE(K > 0, "gemm_wgrad_multi: K=%d", K);
+  GemmMultiMaps mm;
+  memset(&mm, 0, sizeof(mm));
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.K = K;
+  p.accumulate = 1;
+  p.n_prob = n;
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    UB_REQUIRE(pr[i].A && pr[i].B && pr[i].C && pr[i].M > 0 && pr[i].N > 0 && pr[i].N % 8 == 0 && pr[i].M % 8 == 0,
+               "gemm_wgrad_multi: problem %d: null operand or bad shape M=%d N=%d", i, pr[i].M, pr[i].N);
+    if (make_tmap_2d(&mm.a[i], pr[i].A, K, pr[i].M, pr[i].lda, 64, 64, 2)) return 1;       // dY_i  [K tokens, M_i]  (MN-major A)
+    if (make_tmap_2d(&mm.b[i], pr[i].B, K, pr[i].N, pr[i].ldb, 64, 64, 2)) return 1;       // X_i   [K tokens, N_i]  (MN-major B)
+    if (make_tmap_2d(&mm.c[i], pr[i].C, pr[i].M, pr[i].N, pr[i].ldc, 32, 32, 4)) return 1;  // dW_i  [M_i, N_i] fp32
+    p.tile_off[i] = tiles;
+    p.ntile_n[i] = (pr[i].N + 255) / 256;
+    tiles += ((pr[i].M + 2 * BM - 1) / (2 * BM)) * p.ntile_n[i];
+  }
+  for (int i = n; i <= GEMM_MAX_PROB; ++i) p.tile_off[i] = tiles;
+  for (int i = n; i < GEMM_MAX_PROB; ++i) { mm.a[i] = mm.a[0]; mm.b[i] = mm.b[0]; mm.c[i] = mm.c[0]; p.ntile_n[i] = 1; }
+  p.M = pr[0].M; p.N = pr[0].N;                    // unused by the multi-problem schedule (kept sane)
+  const int total_kb = (K + BK - 1) / BK;
+  if (split_k < 1) split_k = 1;
+  if (split_k > total_kb) split_k = total_kb;
+  p.kb_per_split = (total_kb + split_k - 1) / split_k;
+  p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  const long total_work = (long)tiles * p.splits;
+  const int units = sm_count() / 2;
+  const int grid = (int)(total_work < units ? total_work : units) * 2;
+  constexpr int STAGES = 5;
+  constexpr int SMEM = STAGES * (BM * BK * 2 + 128 * BK * 2) + GemmCfg<256, 0, 2>::EPI_BYTES + 2 * 256 * 4 + (2 * STAGES + 4 + 24) * 8 + 16;
+  static_assert(SMEM <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
+  static bool configured = false;
+  auto kern = gemm_multi_kernel<STAGES>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    UB_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(gemm_multi smem=%d): %s", SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mm, p);
+  UB_REQUIRE(e == cudaSuccess, "gemm_multi_kernel launch: %s", cudaGetErrorString(e));
+  return check_launch("gemm_multi_kernel");
+}
 
 extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                             void* C, int64_t ldc, int M, int N, int K, const ub_gemm_epilogue* ep_in, int split_k,

@@ -37,7 +37,10 @@ def _instrument(name, n_kernels):
             r = fn(*a, **k)
             e1.record()
             info = None
-            if name == "gemm":
+            if name == "gemm" and fn.__name__ == "gemm_wgrad_multi":
+                probs = a[0]                          # counted as one GEMM of sum(M_i * N_i) x 1 x K (same 2 M N K flops)
+                info = (sum(gw.shape[0] * gw.shape[1] for _, _, gw in probs), 1, probs[0][0].shape[0], True, True, True)
+            elif name == "gemm":
                 out = a[2]
                 K = k["group"]["K"] if k.get("group") else (a[0].shape[0] if k.get("a_t") else a[0].shape[1])
                 info = (out.shape[0], out.shape[1], K, bool(k.get("a_t")), bool(k.get("b_t")), out.dtype == F32)
@@ -143,6 +146,24 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=
         ep.colsum_out = _p(colsum_out, F32, "colsum_out")
     check(lib.ub_gemm_bf16(pa, lda, int(a_t), pb, ldb, int(b_t), pc, ldc, M, N, K, C.byref(ep), split_k, _stream()), "ub_gemm_bf16")
     return out
+
+
+@_instrument("gemm", 1)
+def gemm_wgrad_multi(problems, split_k=1):
+    """problems: up to four (dy [K, M_i] bf16, x [K, N_i] bf16, gw [M_i, N_i] fp32): gw_i += dy_i^T x_i, one launch."""
+    if not 1 <= len(problems) <= 4:
+        raise _cabi.UBError("gemm_wgrad_multi: 1..4 problems")
+    arr = (_cabi.GemmProblem * len(problems))()
+    K = problems[0][0].shape[0]
+    for i, (dy, x, gw) in enumerate(problems):
+        pa, lda = _p2d(dy, BF16, "wgrad dy")
+        pb, ldb = _p2d(x, BF16, "wgrad x")
+        pc, ldc = _p2d(gw, F32, "wgrad out")
+        if dy.shape[0] != K or x.shape[0] != K or tuple(gw.shape) != (dy.shape[1], x.shape[1]):
+            raise _cabi.UBError(f"gemm_wgrad_multi: problem {i}: dy{tuple(dy.shape)} x{tuple(x.shape)} gw{tuple(gw.shape)}")
+        arr[i].A, arr[i].lda, arr[i].B, arr[i].ldb, arr[i].C, arr[i].ldc = pa, lda, pb, ldb, pc, ldc
+        arr[i].M, arr[i].N = gw.shape
+    check(lib.ub_gemm_wgrad_multi(arr, len(problems), K, split_k, _stream()), "ub_gemm_wgrad_multi")
 
 
 @_instrument("attn_fwd", 1)

@@ -47,6 +47,25 @@ _SIDE_COLSUM = os.environ.get("UB_SIDE_COLSUM", "0") == "1"
 # q_bias / v_bias gradients accumulated by the attention backward kernels while they store dq / dv (ub_attn_bwd's dbias) instead
 # of a separate column-sum pass over dqkv: 12 launches fewer per ViT-B step.  UB_FUSE_QKV_BIAS=0 restores the separate pass.
 _FUSE_QKV_BIAS = os.environ.get("UB_FUSE_QKV_BIAS", "1") == "1"
+# The four weight gradients of a block (fc2, fc1, proj, qkv: same tokens, different widths) as ONE multi-problem launch at the end
+# of the block's backward (ub_gemm_wgrad_multi) instead of four: one prologue / pipeline fill / drain and one wave quantisation
+# on the 74 CTA pairs (108 pair tiles x split-K 2 = 216 items = 2.9 waves) instead of four.  UB_MULTI_WGRAD=0: separate launches.
+_MULTI_WGRAD = os.environ.get("UB_MULTI_WGRAD", "1") == "1"
+
+
+def _multi_splits(problems, units):
+    """split-K factor for a multi-problem weight-gradient launch: fill whole waves of `units` CTA pairs, keep >= 32 k-blocks per item."""
+    tiles = sum(((gw.shape[0] + 255) // 256) * ((gw.shape[1] + 255) // 256) for _, _, gw in problems)
+    kb = (problems[0][0].shape[0] + 63) // 64
+    best, best_eff = 1, 0.0
+    for s_ in range(1, 17):
+        if s_ > 1 and kb // s_ < 32:
+            break
+        items = tiles * s_
+        eff = items / (((items + units - 1) // units) * units)
+        if eff > best_eff + 1e-9:
+            best, best_eff = s_, eff
+    return best
 
 
 def _splits_for(out_rows: int, out_cols: int, sms: int) -> int:
@@ -235,7 +254,13 @@ class ViTTrunk:
         main = torch.cuda.current_stream() if side is not None else None
         side_done = {}
 
+        multi = _MULTI_WGRAD and side is None and ws.dx.is_cuda
+        pending = []                                    # this block's (dy, x, gw) triples, issued as one launch at its end
+
         def wgrad(dy, x_in, gw):
+            if multi:
+                pending.append((dy, x_in, gw))
+                return
             if side is None:
                 return self._wgrad(dy, x_in, gw)
             ev = torch.cuda.Event()
@@ -316,6 +341,9 @@ class ViTTrunk:
             ops.layernorm_bwd(ws.d_h, ws.x_at(l), self.p(b + "norm1.weight"), self.eps, ws.dx, ws.dx,
                               ws.dxs_m[(l - 1) & 1] if emit else None, s_next, N, self.g(b + "norm1.weight"),
                               self.g(b + "norm1.bias"), dsum=next_bias if emit else None)
+            if multi:
+                ops.gemm_wgrad_multi(pending, split_k=_multi_splits(pending, max(1, self.sms // 2)))
+                pending.clear()
             if side is not None:
                 side_done[l] = torch.cuda.Event()
                 side_done[l].record(side)
