@@ -132,3 +132,26 @@ def test_gelu_epilogue_default_and_exact_erf_builds(variant):
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "gelu_variant_check.py")], capture_output=True, text=True, env=env, timeout=300)
     print(r.stdout[-400:])
     assert r.returncode == 0 and "GELU VARIANT OK" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
+
+
+def test_multi_problem_weight_gradient_gemm():
+    """ub_gemm_wgrad_multi: several dW_i += dY_i^T X_i over the same tokens in one launch — ragged widths (TMA clipping), a token
+    count that is not a multiple of the k-block, accumulation into non-zero dW, 1 to 4 problems, several split-K factors."""
+    import torch
+    from unite_b200 import ops
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(11)
+    for K, widths, split in ((10240, [(768, 3072), (3072, 768), (768, 768), (2304, 768)], 2), (1000, [(200, 328), (512, 64), (8, 1032)], 3),
+                             (4096, [(520, 264)], 1), (320, [(128, 128), (384, 512)], 7)):
+        probs, refs = [], []
+        for (M, N) in widths:
+            dy = (torch.randn(K, M, device=dev, generator=g) * 0.5).bfloat16()
+            x = (torch.randn(K, N, device=dev, generator=g) * 0.5).bfloat16()
+            gw = torch.randn(M, N, device=dev, generator=g)
+            refs.append(gw.double() + dy.double().t() @ x.double())
+            probs.append((dy, x, gw))
+        ops.gemm_wgrad_multi(probs, split_k=split)
+        torch.cuda.synchronize()
+        for (dy, x, gw), ref in zip(probs, refs):
+            err = ((gw.double() - ref).norm() / ref.norm()).item()
+            assert err < 2e-5 and torch.isfinite(gw).all(), (K, tuple(gw.shape), split, err)
