@@ -54,15 +54,18 @@ _MULTI_WGRAD = os.environ.get("UB_MULTI_WGRAD", "1") == "1"
 
 
 def _multi_splits(problems, units):
-    """split-K factor for a multi-problem weight-gradient launch: fill whole waves of `units` CTA pairs, keep >= 32 k-blocks per item."""
+    """split-K factor for a multi-problem weight-gradient launch: the SMALLEST one that fills the waves of `units` CTA pairs to
+    >= 93 % (every extra split is another fp32 reduce-add pass over the weight-gradient tiles), >= 32 k-blocks per item."""
     tiles = sum(((gw.shape[0] + 255) // 256) * ((gw.shape[1] + 255) // 256) for _, _, gw in problems)
     kb = (problems[0][0].shape[0] + 63) // 64
     best, best_eff = 1, 0.0
-    for s_ in range(1, 17):
+    for s_ in range(1, 9):
         if s_ > 1 and kb // s_ < 32:
             break
         items = tiles * s_
         eff = items / (((items + units - 1) // units) * units)
+        if eff >= 0.93:
+            return s_
         if eff > best_eff + 1e-9:
             best, best_eff = s_, eff
     return best
