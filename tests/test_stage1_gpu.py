@@ -87,6 +87,29 @@ def test_full_vitb16_stage1_against_oracle():
     _check_step(eng, ref, videos, q, big_grad_only=True)
 
 
+@pytest.mark.parametrize("B,mask_ratio,n_vis", [(1, 0.8, 320), (3, 0.9, 160), (1, 0.75, 392), (3, 0.5, 784)])
+def test_full_vitb16_stage1_odd_batches_and_other_mask_ratios(B, mask_ratio, n_vis):
+    """Edge shapes of the same step: a single clip, an odd number of clips, and mask ratios other than the shipped 0.8 — 0.9 leaves
+    160 visible tokens (half a 128-row tile in every student GEMM and attention item), 0.75 and 0.5 leave 392 / 784, which takes the
+    student's attention (forward with LSE and backward) off the resident S <= 320 kernels onto the streamed long-sequence ones.
+    run_stage1.py:378-393 (the mask ratio only enters through N_vis = P - int(P * ratio) per frame)."""
+    from oracle import unite_oracle as O
+    from oracle.weights import seeded_state
+    from unite_b200.engine import Stage1Engine
+    scfg, tcfg = O.StudentCfg(), O.TeacherCfg()
+    student, teacher = build_student(scfg), build_teacher(tcfg)
+    ssd = seeded_state({k: tuple(v.shape) for k, v in student.state_dict().items()}, 0)
+    tsd = seeded_state({k: tuple(v.shape) for k, v in teacher.state_dict().items()}, 1)
+    student.load_state_dict(ssd); teacher.load_state_dict(tsd)
+    g = torch.Generator().manual_seed(100 + B + n_vis)
+    videos = torch.randn(B, 3, 8, 224, 224, generator=g)
+    q = torch.empty(B * 8, 196).exponential_(1, generator=g)
+    ref = O.stage1_step(ssd, tsd, videos, q, scfg, tcfg, mask_ratio=mask_ratio)
+    assert ref["vis_idx"].shape == (B, n_vis)
+    eng = Stage1Engine(student.cuda().train(), teacher.cuda().eval(), mask_ratio=mask_ratio)
+    _check_step(eng, ref, videos, q, big_grad_only=True)
+
+
 def test_module_api_matches_engine_and_autograd_accumulates():
     """The reference-facing call `model(videos, mask, clip_only=True)` + loss.backward() gives the same numbers as
     the fused engine, and a second backward accumulates into .grad like torch does."""
