@@ -155,3 +155,18 @@ def test_multi_problem_weight_gradient_gemm():
         for (dy, x, gw), ref in zip(probs, refs):
             err = ((gw.double() - ref).norm() / ref.norm()).item()
             assert err < 2e-5 and torch.isfinite(gw).all(), (K, tuple(gw.shape), split, err)
+
+
+def test_gemm_stream_k_tail_matches_the_whole_tile_schedule():
+    """ub_gemm_epilogue.sk_workspace: the tiles of a partial last wave cut along K across all CTA pairs (partial accumulators parked
+    in the workspace, the piece with a tile's last k-block finishes it).  Every epilogue the step uses, ragged M / N / K, fewer
+    tiles than pairs, three-piece tiles, fp16 residual stream, fp32 accumulate: against fp32 torch, against the whole-tile
+    schedule, and bit-identical over repeated launches (the arrival counters must come back to zero).  Off by default in the step
+    (measured slower, profiles/gemm_streamk_r02.md), so it is kept honest here."""
+    m = importlib.import_module("gemm_sk_check")
+    m.results.clear()
+    for kind, M, N, K in (("res32", 10240, 768, 3072), ("nn", 10240, 768, 2304), ("gelu_aux", 10240, 3072, 768), ("dgelu", 10240, 3072, 768),
+                          ("res32", 10100, 776, 3000), ("res16", 10240, 768, 3072), ("acc32", 4096, 1024, 4096), ("nn", 20480, 1024, 1024),
+                          ("plain", 3200, 768, 1024)):
+        assert m.case(kind, M, N, K), m.results[-1]
+    assert sum(r["split"] for r in m.results) >= 8, [(r["kind"], r["M"], r["N"], r["K"], r["split"]) for r in m.results]

@@ -70,7 +70,59 @@ struct GemmParams {
   int n_prob;
   int tile_off[5];
   int ntile_n[4];
+  // stream-K tail (ub_gemm_epilogue.sk_workspace): tiles [sk_first, sk_first + sk_tiles) — the partial last wave — are cut along K
+  // into sk_units contiguous ranges of k-blocks, one per CTA pair; 0 tiles = every tile is computed whole
+  int sk_first, sk_tiles, sk_units;
+  float* sk_ws;             // partial accumulators: [sk tile][2 slots][2 CTAs][8 warps][4096] fp32 after SK_FLAG_BYTES of counters
 };
+
+constexpr int SK_FLAG_BYTES = 8192;          // (sk tile, CTA, warp) arrival counters, zero between launches
+constexpr int SK_MAX_TILES = SK_FLAG_BYTES / (16 * 4);
+constexpr size_t SK_TILE_BYTES = 2 * 2 * 8 * 4096 * sizeof(float);     // two slots of one 256 x 256 fp32 pair tile
+
+// Stream-K tail, the part shared by the kernel, the host and the CPU tests (ub_gemm_sk_schedule).
+// Plan: T tiles on U CTA pairs, KB k-blocks per tile.  The R = T mod U tiles of the partial last wave are cut into `units`
+// contiguous k-block ranges [u W / units, (u + 1) W / units) of their W = R * KB k-blocks, one per pair, each at least half a tile
+// long — so a range touches at most two tiles and a tile is shared by at most three pairs (two workspace slots).  Cost in
+// k-blocks per pair: whole tiles ceil(T / U) * KB, split tail floor(T / U) * KB + ceil(W / units) + a fix-up charge.
+static int64_t g_sk_launches = 0;        // GEMM launches that split their tail (diagnostic: ub_gemm_sk_launches)
+struct SkPlan { int first, tiles, units; };
+__host__ __device__ inline SkPlan sk_plan(int T, int U, int KB, int overhead) {
+  SkPlan pl{0, 0, 0};
+  if (T <= 0 || U <= 0 || KB < 4) return pl;
+  const int R = T % U;
+  if (R == 0 || R > SK_MAX_TILES) return pl;
+  long us = ((long)R * KB) / ((KB + 1) / 2);
+  if (us > U) us = U;
+  const long dp_cost = (long)((T + U - 1) / U) * KB;
+  const long sk_cost = (long)(T / U) * KB + ((long)R * KB + us - 1) / us + overhead;
+  if (sk_cost >= dp_cost || us < R) return pl;
+  pl.first = T - R; pl.tiles = R; pl.units = (int)us;
+  return pl;
+}
+// Pair u's share: n_dp whole tiles (u, u + U, ... below pl.first), at most one partial piece (k-blocks [part_kb0, part_kb1) of
+// part_tile, parked in slot part_slot) and at most one finishing piece (k-blocks [fin_kb0, KB) of fin_tile, which adds fin_wait
+// parked pieces: slots 0 .. fin_wait - 1).  The piece holding a tile's LAST k-block finishes it.
+struct SkShare { int n_dp, part_tile, part_kb0, part_kb1, part_slot, fin_tile, fin_kb0, fin_wait; };
+__host__ __device__ inline SkShare sk_share(const SkPlan& pl, int u, int U, int KB) {
+  SkShare sh{0, -1, 0, 0, 0, -1, 0, 0};
+  sh.n_dp = u < pl.first ? (pl.first - u + U - 1) / U : 0;
+  if (u >= pl.units) return sh;
+  const long W = (long)pl.tiles * KB;
+  const int s = (int)(((long)u * W) / pl.units), e = (int)(((long)(u + 1) * W) / pl.units);
+  const int ta = s / KB, tb = (e - 1) / KB;
+  const int uf = (int)((((long)ta * KB + 1) * pl.units - 1) / W);          // the pair whose range holds k-block 0 of tile ta
+  const int a0 = s - ta * KB;
+  if (tb > ta) {                       // tail of ta (finishes it) + head of the next tile (partial, slot 0)
+    sh.fin_tile = pl.first + ta; sh.fin_kb0 = a0; sh.fin_wait = u - uf;
+    sh.part_tile = pl.first + tb; sh.part_kb0 = 0; sh.part_kb1 = e - tb * KB; sh.part_slot = 0;
+  } else if (e - ta * KB == KB) {      // reaches the end of ta: finishes it
+    sh.fin_tile = pl.first + ta; sh.fin_kb0 = a0; sh.fin_wait = u - uf;
+  } else {                             // strictly inside ta (or its head): partial, slot = position among the tile's pieces
+    sh.part_tile = pl.first + ta; sh.part_kb0 = a0; sh.part_kb1 = e - ta * KB; sh.part_slot = u - uf;
+  }
+  return sh;
+}
 
 constexpr int GEMM_MAX_PROB = 4;
 struct GemmMultiMaps {
@@ -174,13 +226,50 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   };
   const int w_first = blockIdx.x / NCTA, w_step = gridDim.x / NCTA;   // both CTAs of a pair walk the same work items
 
+  // ---- this pair's list of work items.  Ordinarily item i is work index w_first + i * w_step = (tile, k-split).  With a
+  // stream-K tail (p.sk_tiles > 0; CTA pairs on 256 x 256 tiles only; sk_plan / sk_share above) the pair works in the order
+  // [partial piece] [its whole tiles] [finishing piece]: partial accumulators (fp32, parked in the workspace by the epilogue warps
+  // and announced through a per-(tile, CTA, warp) counter) are written at the start of the kernel and consumed at its end, so the
+  // wait is off the critical path and cannot form a cycle (a partial piece waits for nothing).
+  constexpr bool SK_OK = NCTA == 2 && BN == 256 && !MULTI;
+  const bool sk = SK_OK && p.sk_tiles > 0;
+  int n_items, n_dp = 0;
+  int part_tile = -1, part_kb0 = 0, part_kb1 = 0, part_slot = 0;      // this pair's partial piece (at most one)
+  int fin_tile = -1, fin_kb0 = 0, fin_wait = 0;                        // this pair's finishing piece (at most one)
+  if (sk) {
+    const SkShare sh = sk_share(SkPlan{p.sk_first, p.sk_tiles, p.sk_units}, w_first, w_step, total_kb);
+    n_dp = sh.n_dp;
+    part_tile = sh.part_tile; part_kb0 = sh.part_kb0; part_kb1 = sh.part_kb1; part_slot = sh.part_slot;
+    fin_tile = sh.fin_tile; fin_kb0 = sh.fin_kb0; fin_wait = sh.fin_wait;
+    n_items = (part_tile >= 0 ? 1 : 0) + n_dp + (fin_tile >= 0 ? 1 : 0);
+  } else {
+    n_items = w_first < total_work ? (total_work - w_first + w_step - 1) / w_step : 0;
+  }
+  const int n_part = (sk && part_tile >= 0) ? 1 : 0;              // the partial piece comes first in the list
+  // item i -> (tile, k-block range, kind: 0 whole tile / k-split item, 1 partial piece (aux = slot), 2 finishing piece (aux = pieces to add))
+  auto get_item = [&](int i, int& tile, int& kb0, int& kb1, int& kind, int& aux) {
+    if (!sk) {
+      const int w = w_first + i * w_step, ks = w % p.splits;
+      tile = w / p.splits;
+      kb0 = ks * p.kb_per_split;
+      kb1 = min(total_kb, kb0 + p.kb_per_split);
+      kind = 0; aux = 0;
+    } else if (i < n_part) {
+      tile = part_tile; kb0 = part_kb0; kb1 = part_kb1; kind = 1; aux = part_slot;
+    } else if (i < n_part + n_dp) {
+      tile = w_first + (i - n_part) * w_step; kb0 = 0; kb1 = total_kb; kind = 0; aux = 0;
+    } else {
+      tile = fin_tile; kb0 = fin_kb0; kb1 = total_kb; kind = fin_wait > 0 ? 2 : 0; aux = fin_wait;
+    }
+  };
+
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int w = w_first; w < total_work; w += w_step) {
-      const int ks = w % p.splits;
-      const int tile = w / p.splits;
+    for (int it = 0; it < n_items; ++it) {
+      int tile, kb0, kb1, kind, aux;
+      get_item(it, tile, kb0, kb1, kind, aux);
       int pi, tm, tn;
       decode(tile, pi, tm, tn);
       const CUtensorMap* pA = MULTI ? &mm->a[pi] : &tmA;
@@ -189,8 +278,6 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
       const int m0 = tm * (BM * NCTA) + (int)cta_rank * BM - grp * p.a_m_off;      // this CTA's rows of A
       const int n0 = tn * BN + (int)pr * BN_L + grp * p.b_n_off;                   // this CTA's rows of B
       const int ka = grp * p.a_k_off, kbo = grp * p.b_k_off;                                     // K offsets of the group
-      const int kb0 = ks * p.kb_per_split;
-      const int kb1 = min(total_kb, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (lane == 0) {
@@ -246,10 +333,9 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     uint32_t phase = 0;
     int as = 0;
     uint32_t aphase = 0;
-    for (int w = w_first; w < total_work; w += w_step) {
-      const int ks = w % p.splits;
-      const int kb0 = ks * p.kb_per_split;
-      const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+    for (int it = 0; it < n_items; ++it) {
+      int tile, kb0, kb1, kind, aux;
+      get_item(it, tile, kb0, kb1, kind, aux);
       if (NCTA >= 2) mbar_wait_cluster(&tempty[as], aphase ^ 1); else mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -298,33 +384,74 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
     int as = 0;
     uint32_t aphase = 0;
     uint32_t cc = 0;                    // running slab counter of this warp: staging buffer = cc & 1
-    // (row, col) of this warp's slab `c` of work item `w`
-    auto slab_row = [&](int w) {
+    // (row, col) of this warp's slab `c` of work item `i`
+    auto item_tile = [&](int i) {
+      int tile, kb0, kb1, kind, aux;
+      get_item(i, tile, kb0, kb1, kind, aux);
+      return tile;
+    };
+    auto slab_row = [&](int i) {
       int pi, tm, tn;
-      decode(w / p.splits, pi, tm, tn);
+      decode(item_tile(i), pi, tm, tn);
       return tm * (BM * NCTA) + (int)cta_rank * BM + sp * 32;
     };
-    auto slab_col = [&](int w, int c) {
+    auto slab_col = [&](int i, int c) {
       int pi, tm, tn;
-      decode(w / p.splits, pi, tm, tn);
+      decode(item_tile(i), pi, tm, tn);
       return tn * BN + half * (BN / 2) + c * CW;
     };
-    if (EPI != 0 && w_first < total_work && lane == 0) {
+    // the partial piece of a stream-K tail comes first and uses neither the staging slabs nor the operand prefetch chain
+    if (EPI != 0 && n_part < n_items && lane == 0) {
       // residual / pre-activation slabs of the first NBUF - 1 (tile, slab) pairs of this warp
       mbar_expect_tx(&rb[0], 4096);
-      tma_load_2d(&tmR, &rb[0], slab0, slab_col(w_first, 0), slab_row(w_first));
+      tma_load_2d(&tmR, &rb[0], slab0, slab_col(n_part, 0), slab_row(n_part));
       if (NBUF == 3) {
-        int nw = w_first, nc = 1;
-        if (nc == SLABS) { nc = 0; nw += w_step; }
-        if (nw < total_work) {
+        int ni = n_part, nc = 1;
+        if (nc == SLABS) { nc = 0; ++ni; }
+        if (ni < n_items) {
           mbar_expect_tx(&rb[1], 4096);
-          tma_load_2d(&tmR, &rb[1], slab0 + 4096, slab_col(nw, nc), slab_row(nw));
+          tma_load_2d(&tmR, &rb[1], slab0 + 4096, slab_col(ni, nc), slab_row(ni));
         }
       }
     }
-    for (int w = w_first; w < total_work; w += w_step) {
+    // this warp's corner of the stream-K workspace: a [32 rows x 128 columns] fp32 block per (sk tile, slot, CTA, warp), stored as
+    // four 32 x 32 sub-blocks in register order (float4 j of lane l at (j * 32 + l) * 16 bytes: 512 contiguous bytes per access)
+    uint32_t* const sk_flags = reinterpret_cast<uint32_t*>(p.sk_ws);
+    float* const sk_data = p.sk_ws + SK_FLAG_BYTES / 4;
+    if (SK_OK && n_part) {
+      // ---- partial piece: accumulators -> workspace, then announce them
+      const int ti = part_tile - p.sk_first;
+      float* dst = sk_data + (size_t)((((ti * 2 + part_slot) * 2 + (int)pr) * 8 + we)) * 4096 + lane * 4;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(sp * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
+#pragma unroll 1
+      for (int blk = 0; blk < (BN / 2) / 32; ++blk) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + (uint32_t)(blk * 32), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.global.cg.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst + blk * 1024 + j * 128), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                       "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                       : "memory");
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        atomicAdd(sk_flags + (ti * 2 + (int)pr) * 8 + we, 1u);
+        if (NCTA >= 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[as]), leader_rank)); else mbar_arrive(&tempty[as]);
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+    for (int it = n_part; it < n_items; ++it) {
+      int w_tile, w_kb0, w_kb1, w_kind, w_aux;
+      get_item(it, w_tile, w_kb0, w_kb1, w_kind, w_aux);
       int w_pi, w_tm, w_tn;
-      decode(w / p.splits, w_pi, w_tm, w_tn);
+      decode(w_tile, w_pi, w_tm, w_tn);
+      const int w = it;       // slab_row / slab_col take the item index
       const CUtensorMap* pC = MULTI ? &mm->c[w_pi] : &tmC;
       const int n0 = w_tn * BN;
       const int row0 = slab_row(w);
@@ -350,6 +477,42 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
         }
       }
       float st1 = 0.0f, st2 = 0.0f;             // EPI 3: row statistics of the fp16 values this thread writes
+      // finishing piece of a stream-K tile: the other pieces' accumulators for the next 32 x 32 block travel one block ahead
+      float4 skp[SK_OK ? 8 : 1];
+      const float* sk_src = nullptr;
+      const int sk_add = (SK_OK && w_kind == 2) ? w_aux : 0;
+      auto sk_fetch = [&](int blk) {
+#pragma unroll
+        for (int j = 0; j < (SK_OK ? 8 : 1); ++j) {
+          const float* a = sk_src + blk * 1024 + j * 128;
+          asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(skp[j].x), "=f"(skp[j].y), "=f"(skp[j].z), "=f"(skp[j].w) : "l"(a) : "memory");
+        }
+        if (sk_add > 1) {
+#pragma unroll
+          for (int j = 0; j < (SK_OK ? 8 : 1); ++j) {
+            float4 t;
+            const float* a = sk_src + 2 * 8 * 4096 + blk * 1024 + j * 128;     // slot 1
+            asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(a) : "memory");
+            skp[j].x += t.x; skp[j].y += t.y; skp[j].z += t.z; skp[j].w += t.w;
+          }
+        }
+      };
+      if (SK_OK && sk_add > 0) {
+        const int ti = w_tile - p.sk_first;
+        uint32_t* flag = sk_flags + (ti * 2 + (int)pr) * 8 + we;
+        if (lane == 0) {
+          uint32_t seen;
+          const long long t0 = clock64();
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+            if ((int)seen < sk_add && clock64() - t0 > 20000000000ll) __trap();      // ~10 s: a partial piece never arrived
+          } while ((int)seen < sk_add);
+          *flag = 0u;          // zero again for the next launch (nobody else touches it any more in this one)
+        }
+        __syncwarp();
+        sk_src = sk_data + (size_t)(((ti * 2) * 2 + (int)pr) * 8 + we) * 4096 + lane * 4;
+        sk_fetch(0);
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(sp * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
@@ -370,8 +533,8 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
           if (lane == 0) {
             tma_store_wait_read<0>();
             int nw = w, nc = c + (NBUF - 1);
-            while (nc >= SLABS) { nc -= SLABS; nw += w_step; }
-            if (nw < total_work) {
+            while (nc >= SLABS) { nc -= SLABS; ++nw; }
+            if (nw < n_items) {
               const int nb = NBUF == 3 ? (int)((cc + 2u) % 3u) : (b ^ 1);
               mbar_expect_tx(&rb[nb], 4096);
               tma_load_2d(&tmR, &rb[nb], slab0 + (nb << 12), slab_col(nw, nc), slab_row(nw));
@@ -398,6 +561,14 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (SK_OK && sk_add > 0) {
+#pragma unroll
+            for (int j = 0; j < (SK_OK ? 8 : 1); ++j) {
+              v[4 * j] += skp[j].x; v[4 * j + 1] += skp[j].y; v[4 * j + 2] += skp[j].z; v[4 * j + 3] += skp[j].w;
+            }
+            const int blk = c * (CW / 32) + h + 1;
+            if (blk < (BN / 2) / 32) sk_fetch(blk);
+          }
           if (EPI == 0 && p.ln_stats != nullptr) {
             const float2 rs2 = make_float2(ln_rstd, ln_rstd), nrm2 = make_float2(-ln_rm, -ln_rm);
 #pragma unroll
@@ -729,6 +900,21 @@ static int launch_gemm(const GemmMaps& m, const GemmParams& p, int epi, bool out
 }  // namespace ub
 
 extern "C" int ub_gemm_cluster4_capacity(void) { return ub::max_clusters4(); }
+extern "C" int64_t ub_gemm_sk_launches(void) { return ub::g_sk_launches; }
+// test hook: the stream-K plan for T tiles on U pairs with KB k-blocks per tile and pair u's share of it, as the kernel computes them
+// out = {first, tiles, units, n_dp, part_tile, part_kb0, part_kb1, part_slot, fin_tile, fin_kb0, fin_wait}; returns 1 if the tail is split
+extern "C" int ub_gemm_sk_schedule(int T, int U, int KB, int overhead, int u, int32_t* out) {
+  const ub::SkPlan pl = ub::sk_plan(T, U, KB, overhead);
+  const ub::SkShare sh = ub::sk_share(pl, u, U, KB);
+  const int32_t v[11] = {pl.first, pl.tiles, pl.units, sh.n_dp, sh.part_tile, sh.part_kb0, sh.part_kb1, sh.part_slot, sh.fin_tile, sh.fin_kb0, sh.fin_wait};
+  if (out) memcpy(out, v, sizeof(v));
+  return pl.tiles > 0 ? 1 : 0;
+}
+extern "C" int64_t ub_gemm_sk_workspace_bytes(void) {
+  // the tail of a persistent schedule on sms / 2 CTA pairs holds at most sms / 2 - 1 tiles
+  const int64_t tiles = ub::sm_count() / 2 < ub::SK_MAX_TILES ? ub::sm_count() / 2 : ub::SK_MAX_TILES;
+  return ub::SK_FLAG_BYTES + tiles * (int64_t)ub::SK_TILE_BYTES;
+}
 
 extern "C" int ub_gemm_wgrad_multi(const ub_gemm_problem* pr, int n, int K, int split_k, void* stream) {
   using namespace ub;
@@ -917,11 +1103,30 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   const long total_work = (long)((M + BM * ncta - 1) / (BM * ncta)) * ((N + bn - 1) / bn) * split_k;
   int units = ncta == 4 ? units4 : sms / ncta;
   if (ep.max_ctas > 0 && ep.max_ctas / ncta >= 1 && ep.max_ctas / ncta < units) units = ep.max_ctas / ncta;
-  // max_ctas < 0: one CTA (pair) per work item — a NON-persistent grid.  Meant for GEMMs that are off the critical path (weight
-  // gradients) and run on a low-priority stream: their short-lived CTAs fill SMs the critical path leaves idle, and the block
-  // scheduler can hand an SM back to the high-priority stream at every CTA boundary instead of after a whole static tile list.
-  if (ep.max_ctas < 0) units = (int)(total_work < 65535 ? total_work : 65535);
-  const int grid = (int)(total_work < units ? total_work : units) * ncta;
+  // stream-K tail: when the last wave of 256 x 256 pair tiles is partial, cut its R tiles along K over all the pairs.  Time in
+  // k-blocks per pair: whole tiles ceil(T / U) * KB; with the tail split floor(T / U) * KB + ceil(R * KB / U') + a fix-up charge
+  // (the partial accumulators' round trip through L2 and the finishing epilogue that waits for them; UB_GEMM_SK_OVERHEAD, in
+  // k-blocks).  U' <= U keeps every range at least half a tile long (at most three pieces per tile, two workspace slots).
+  p.sk_first = p.sk_tiles = p.sk_units = 0;
+  p.sk_ws = nullptr;
+  static int sk_overhead = -1;
+  if (sk_overhead < 0) {
+    const char* o = getenv("UB_GEMM_SK_OVERHEAD");
+    sk_overhead = o ? atoi(o) : 4;
+    if (sk_overhead < 0) sk_overhead = 0;
+  }
+  if (ep.sk_workspace != nullptr && ncta == 2 && bn == 256 && split_k == 1 && ep.group_rows == 0 && ep.max_ctas >= 0 &&
+      total_work > 0 && total_work < (1l << 30)) {
+    const SkPlan pl = sk_plan((int)total_work, units, total_kb, sk_overhead);
+    const int64_t need = SK_FLAG_BYTES + (int64_t)pl.tiles * (int64_t)SK_TILE_BYTES;
+    if (pl.tiles > 0 && ep.sk_workspace_bytes >= need && (reinterpret_cast<uintptr_t>(ep.sk_workspace) & 15) == 0) {
+      p.sk_first = pl.first; p.sk_tiles = pl.tiles; p.sk_units = pl.units;
+      p.sk_ws = reinterpret_cast<float*>(ep.sk_workspace);
+      ++g_sk_launches;
+    }
+  }
+  int grid = (int)(total_work < units ? total_work : units) * ncta;
+  if (p.sk_tiles > 0) grid = (p.sk_first > 0 ? units : p.sk_units) * ncta;      // every pair of the split takes part
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
 #define UB_GEMM_CASE(AMN, BMN)                                                                       \
