@@ -496,3 +496,77 @@ def test_four_training_steps_track_the_oracle_with_torch_adamw():
         worst_cos = min(worst_cos, cosine(sd[k].detach().cpu() - ssd[k], p.detach() - ssd[k]))
     print(f"after 4 steps: worst weight rel-L2 {worst:.2e}, worst update cosine {worst_cos:.4f}")
     assert worst < 2e-2 and worst_cos >= 0.97
+
+
+# ---- CUDA-graph replay of the stage-2 / stage-3 steps ---------------------------------------------------------------------------
+def test_stage2_graph_replay_matches_eager_steps():
+    """Stage2Engine(use_graph=True): two eager steps, then one captured graph per resident batch, replayed — against an identical
+    engine that runs every step eagerly (same weights, same DropPath seed, layer-decay groups, clip_grad on): per-step losses,
+    running statistics and the weights after 7 updates agree to accumulation-order noise."""
+    from unite_b200.engine_for_finetuning import Stage2Engine
+    from unite_b200.optim_factory import LayerDecayValueAssigner, create_optimizer
+    fix, scfg, *_ = _tiny()
+    _, _, vsd = seeded_states(fix)
+    g = torch.Generator().manual_seed(77)
+    shape = (3, scfg.num_frames, scfg.img_size, scfg.img_size)
+    batches = [(torch.randn(6, *shape, generator=g).cuda(), torch.randint(0, scfg.num_classes, (6,), generator=g).cuda()) for _ in range(2)]
+
+    class Args:
+        opt, lr, weight_decay, opt_betas, opt_eps = "adamw", 2e-3, 0.05, (0.9, 0.999), 1e-8
+    runs = []
+    for use_graph in (True, False):
+        vit = _build_vit(scfg, drop_path_rate=0.2)
+        vit.load_state_dict(vsd, strict=True)
+        vit = vit.cuda().train()
+        L = vit.get_num_layers()
+        asg = LayerDecayValueAssigner([0.65 ** (L + 1 - i) for i in range(L + 2)])
+        opt = create_optimizer(Args, vit, get_num_layer=asg.get_layer_id, get_layer_scale=asg.get_scale)
+        eng = Stage2Engine(vit, opt, use_graph=use_graph)
+        eng.max_norm = 1.0
+        losses = []
+        for s in range(7):
+            for grp in opt.param_groups:                                          # a schedule: the graph must read lr from device memory
+                grp["lr"] = 2e-3 * (1 + s) / 7 * grp["lr_scale"]
+            losses.append(eng.step(*batches[s % 2]).clone())
+        torch.cuda.synchronize()
+        runs.append((torch.cat(losses).cpu(), eng.stats.cpu(), vit.core().arena.params.clone().cpu(), eng))
+    (l_g, st_g, p_g, eng_g), (l_e, st_e, p_e, _) = runs
+    assert len(eng_g.graphs._graphs) == 2, "one graph per resident batch expected"
+    assert int(eng_g.core.drop_path.step.item()) == 7, "capture must not consume a DropPath draw"
+    assert torch.allclose(l_g, l_e, rtol=2e-5, atol=0), (l_g, l_e)
+    assert len(set(round(v, 5) for v in l_g.tolist())) >= 6, "replays did not see fresh DropPath factors / weights"
+    assert torch.allclose(st_g, st_e, rtol=1e-4), (st_g, st_e)
+    assert rel_l2(p_g, p_e) < 1e-5
+
+
+def test_stage3_graph_replay_matches_eager_steps():
+    """Stage3Engine(use_graph=True) against the eager engine: the five forwards, both backwards and AdamW of 6 updates (dual-view
+    target batch, DropPath 0.2 in every pass) replayed from the graph give the same losses and weights."""
+    from unite_b200.engine_stage3 import Stage3Engine
+    fix, scfg, tcfg, ssd, tsd, *_ = _tiny()
+    C, D = 12, scfg.embed_dim
+    g = torch.Generator().manual_seed(31)
+    cls_w, cls_b, text = torch.randn(C, D, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1, torch.randn(C, tcfg.output_dim, generator=g)
+    shape = (3, scfg.num_frames, scfg.img_size, scfg.img_size)
+    batches = []
+    for _ in range(2):
+        vt = torch.randn(4, *shape, generator=g)
+        batches.append((torch.randn(4, *shape, generator=g).cuda(), torch.randint(0, C, (4,), generator=g).cuda(), vt.cuda(),
+                        (vt + 0.1 * torch.randn(4, *shape, generator=g)).cuda()))
+    runs = []
+    for use_graph in (True, False):
+        student, teacher = build_student(scfg, drop_path_rate=0.2), build_teacher(tcfg)
+        student.load_state_dict(ssd, strict=True)
+        teacher.load_state_dict(tsd, strict=True)
+        eng = Stage3Engine(student.cuda().train(), teacher.cuda().eval(), cls_w, cls_b, text, mask_ratio=0.75, k=2, lr=1e-3, use_graph=use_graph)
+        losses = []
+        for s in range(6):
+            eng.step(*batches[s % 2])
+            losses.append(torch.cat([eng.loss, eng.loss_s, eng.loss_t]).clone())
+        torch.cuda.synchronize()
+        runs.append((torch.stack(losses).cpu(), eng.core.arena.params.clone().cpu(), eng))
+    (l_g, p_g, eng_g), (l_e, p_e, _) = runs
+    assert len(eng_g.graphs._graphs) == 2
+    assert torch.allclose(l_g, l_e, rtol=5e-5, atol=1e-7), (l_g, l_e)
+    assert rel_l2(p_g, p_e) < 1e-5
+    assert eng_g.last["sel_mask"].shape[0] == 4 and torch.isfinite(eng_g.last["logits_masked"]).all()

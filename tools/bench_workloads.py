@@ -42,10 +42,10 @@ def run_workload(args, rank, local, world, dev, ClockSampler, measured_peaks, F_
     g = torch.Generator().manual_seed(1000 + rank)
     unit = "clips/s"
     extra = {}
+    use_graph = os.environ.get("UB_NO_GRAPH", "0") != "1"
     if wl == "stage2":
         from unite_b200.registry import create_model
         from unite_b200 import modeling_finetune  # noqa: F401
-        from unite_b200.engine_for_finetuning import finetune_step
         from unite_b200.optim_factory import LayerDecayValueAssigner, create_optimizer
         torch.manual_seed(0)
         # run_stage2.py:328-346 with configs/stage2_config.yaml
@@ -61,29 +61,26 @@ def run_workload(args, rank, local, world, dev, ClockSampler, measured_peaks, F_
         if gs is not None:
             gs.arena = model.core().arena
         batches = [(torch.randn(B, 3, 8, 224, 224, generator=g).to(dev), torch.randint(0, 12, (B,), generator=g).to(dev)) for _ in range(2)]
-        loss = torch.zeros(1, device=dev)
+        from unite_b200.engine_for_finetuning import Stage2Engine
+        eng = Stage2Engine(model, opt, grad_sync=gs, use_graph=use_graph)
         i = [0]
 
         def step():
             v, y = batches[i[0] % 2]
             i[0] += 1
-            opt.zero_grad()
-            loss.zero_()
-            finetune_step(model, v, y, loss, grad_sync=gs)
-            scale = gs.all_reduce(model.core().arena.grads) if gs is not None else 1.0
-            opt.step(grad_scale=scale)
-            return loss
+            return eng.step(v, y)
         metric = "clips/sec (ViT-B/16 8x224^2 stage-2 supervised step, 1568 tokens)"
         workload = ("BASELINE configs[0] shape on the GPU: stage-2 supervised fine-tune, ViT-B/16 on all 1568 tokens, CE, drop_path 0.1, "
                     "AdamW with layer decay 0.65 (14 x 2 groups)")
         extra["optimizer_groups"] = len(opt.param_groups)
+        extra["cuda_graph"] = use_graph
     elif wl == "stage3":
         from unite_b200.engine_stage3 import Stage3Engine
         student, teacher = bench.build_models(seed=0)
         student, teacher = student.to(dev).train(), teacher.to(dev).eval()
         gw = torch.Generator().manual_seed(5)
         eng = Stage3Engine(student, teacher, torch.randn(12, 768, generator=gw) * 0.5, torch.zeros(12), torch.randn(12, 512, generator=gw),
-                           mask_ratio=0.8, k=2, grad_sync=gs)
+                           mask_ratio=0.8, k=2, grad_sync=gs, use_graph=use_graph)
         if gs is not None:
             gs.arena = eng.core.arena
         mk = lambda: torch.randn(B, 3, 8, 224, 224, generator=g)
@@ -101,13 +98,14 @@ def run_workload(args, rank, local, world, dev, ClockSampler, measured_peaks, F_
         workload = ("BASELINE configs[3]: stage-3 step per (source, target) pair — teacher attention on vid_aug + zero-shot CLS on vid, source "
                     "full pass (grad), target full pass, k=2 masked committee (last member trains), MatchOrConf fusion, AdamW; drop_path 0.1")
         extra["per_gpu_pairs"] = B
+        extra["cuda_graph"] = use_graph
         extra["ddp"] = "fused NVLink step" if getattr(eng, "nvls", None) is not None else ("NCCL all-reduce" if world > 1 else "n/a")
     else:
         from unite_b200.engine import Stage1Engine
         student, teacher = bench.build_models(seed=0, large=True)
         student, teacher = student.to(dev).train(), teacher.to(dev).eval()
-        eng = Stage1Engine(student, teacher, mask_ratio=0.8, lr=1.5e-4 * B * world / 256, grad_sync=gs,
-                           use_graph=os.environ.get("UB_NO_GRAPH", "0") != "1")
+        eng = Stage1Engine(student, teacher, mask_ratio=0.8, lr=1.5e-4 * B * world / 256, grad_sync=gs, use_graph=use_graph)
+        extra["cuda_graph"] = use_graph
         if gs is not None:
             gs.arena = eng.core.arena
         batches = [(v.to(dev), q.to(dev)) for v, q in bench.host_batches(B, rank, frames=16, tokens_per_frame=2)]

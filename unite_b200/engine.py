@@ -204,6 +204,62 @@ class FusedAdamW:
             g.update({k: v for k, v in saved.items() if k != "params"})
 
 
+class GraphReplay:
+    """CUDA-graph plumbing shared by the stage-2 and stage-3 engines (Stage1Engine.step carries the same logic inline): the first
+    two steps of an input signature run eagerly (lazy attribute setting, workspace allocation, NCCL initialisation), then the
+    step body is captured once per set of persistent input buffers — callers that cycle through a few resident buffers get one
+    graph per buffer set, bound directly to them; past `max_graphs` sets the inputs are copied into one more graph that owns
+    private static inputs.  All graphs share one memory pool (they never run concurrently).  The body must be free of host
+    synchronisation and read its per-step scalars from device memory (FusedAdamW.prepare_step / step_dev)."""
+
+    def __init__(self, max_graphs: Optional[int] = None):
+        self.max_graphs = int(os.environ.get("UB_MAX_GRAPHS", "6")) if max_graphs is None else max_graphs
+        self._graphs, self._count, self._eager, self._pool = {}, {}, {}, None
+
+    def clear(self):
+        self._graphs.clear(); self._count.clear()
+
+    def run(self, shape_key, inputs, body, state_fn=None, private=False):
+        """inputs: tuple of device tensors (None entries are passed through).  body(*inputs) runs one step.  state_fn() -> any
+        object describing the tensors the body left behind (captured once per graph, returned on every replay).
+        private=True: always replay the graph with private static inputs (for callers whose batches arrive in fresh tensors)."""
+        n = self._eager.get(shape_key, 0)
+        if n < 2:
+            self._eager[shape_key] = n + 1
+            body(*inputs)
+            return state_fn() if state_fn else None
+        ptrs = tuple(t.data_ptr() if t is not None else 0 for t in inputs)
+        buf_key = shape_key + (("private",) if private else ptrs)
+        if buf_key not in self._graphs:
+            private = private or self._count.get(shape_key, 0) >= self.max_graphs
+            if private:
+                buf_key = shape_key + ("private",)
+            if buf_key not in self._graphs:
+                static = tuple((torch.empty_like(t) if t is not None else None) for t in inputs) if private else tuple(inputs)
+                if private:
+                    for s_, t in zip(static, inputs):
+                        if t is not None:
+                            s_.copy_(t)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = ops.LAUNCHES
+                with torch.cuda.graph(g, pool=self._pool):
+                    body(*static)
+                if self._pool is None:
+                    self._pool = g.pool()
+                n_kernels = ops.LAUNCHES - n0           # kernels of ours recorded in the graph (capture executes nothing)
+                ops.LAUNCHES = n0
+                self._graphs[buf_key] = (g, static, n_kernels, state_fn() if state_fn else None)
+                self._count[shape_key] = self._count.get(shape_key, 0) + 1
+        g, static, n_kernels, state = self._graphs[buf_key]
+        ops.LAUNCHES += n_kernels                       # every replay launches all of them
+        for s_, t in zip(static, inputs):
+            if t is not None and s_.data_ptr() != t.data_ptr():
+                s_.copy_(t, non_blocking=True)
+        g.replay()
+        return state
+
+
 def require_fused_optimizer(optimizer, arena, what: str):
     """The engines update the arena with FusedAdamW only.  A foreign optimizer (torch.optim.AdamW from the reference's
     create_optimizer, src/optim_factory.py:120-175) would silently be ignored — refuse it instead."""

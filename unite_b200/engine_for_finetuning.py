@@ -49,6 +49,62 @@ def finetune_step(model, samples, targets, loss_acc, scale=1.0, grad_sync=None):
     return logits
 
 
+class Stage2Engine:
+    """One whole stage-2 update (update_freq == 1): zero the gradient arena, forward, CE, backward, gradient all-reduce, grad-norm +
+    layer-decay AdamW — engine_for_finetuning.py:116-127 — replayed from a CUDA graph after two eager steps (engine.GraphReplay):
+    the ~750 launches of the all-token step then cost one launch.  DropPath draws come from the device-side generator, the
+    optimizer's lr / wd / bias corrections from device memory (FusedAdamW.prepare_step), so nothing in the body depends on the
+    host.  The running sums train_one_epoch reports (loss, correct predictions, grad-norm) are accumulated on the device inside
+    the step."""
+
+    def __init__(self, model, optimizer: FusedAdamW, grad_sync=None, use_graph: bool = False):
+        from .engine import GraphReplay
+        self.model = model
+        self.net = model.module if hasattr(model, "module") else model
+        self.core = self.net.core()
+        self.optimizer = require_fused_optimizer(optimizer, self.core.arena, "Stage2Engine")
+        self.grad_sync = grad_sync
+        self.use_graph = use_graph
+        self.max_norm = None
+        dev = self.core.arena.device
+        self.loss = torch.zeros(1, device=dev)
+        self.stats = torch.zeros(3, device=dev)             # running sums: loss, correct predictions, grad-norm
+        self.graphs = GraphReplay()
+        self.logits = None
+
+    def _body(self, samples, targets):
+        self.optimizer.zero_grad()
+        self.loss.zero_()
+        logits = finetune_step(self.model, samples, targets, self.loss, scale=1.0, grad_sync=self.grad_sync)
+        if self.grad_sync is not None:
+            self.grad_sync.all_reduce(self.core.arena.grads)
+        self.optimizer.step_dev(max_norm=self.max_norm)
+        scale = 1.0 / self.grad_sync.world if self.grad_sync is not None else 1.0
+        self.stats += torch.cat([self.loss, (logits.argmax(-1) == targets).sum().float().view(1), self.optimizer.grad_norm(scale)])
+        self.logits = logits
+
+    def step(self, samples, targets, private_inputs=False):
+        """samples fp32 [B,3,T,H,W], targets integer [B], both on the device.  Returns the device loss tensor [1].
+        private_inputs: the batch lives in fresh tensors every step (a loader), so the graph keeps its own static inputs."""
+        scale = 1.0 / self.grad_sync.world if self.grad_sync is not None else 1.0
+        self.optimizer.prepare_step(grad_scale=scale)
+        if not self.use_graph:
+            self._body(samples, targets)
+            return self.loss
+        key = (tuple(samples.shape), samples.dtype, targets.dtype, float(self.max_norm or 0.0), bool(self.net.training))
+        self.logits = self.graphs.run(key, (samples, targets), self._body, state_fn=lambda: self.logits, private=private_inputs)
+        return self.loss
+
+
+def _stage2_engine(model, net, optimizer, gs):
+    held = net.__dict__.get("_ub_stage2_engine")
+    if held is None or held.optimizer is not optimizer or held.grad_sync is not gs:
+        import os
+        held = Stage2Engine(model, optimizer, grad_sync=gs, use_graph=os.environ.get("UB_NO_GRAPH", "0") != "1")
+        net.__dict__["_ub_stage2_engine"] = held
+    return held
+
+
 def train_one_epoch(model: torch.nn.Module, criterion=None, data_loader: Iterable = (), optimizer=None, device=None, epoch: int = 0,
                     loss_scaler=None, max_norm: float = 0, model_ema=None, mixup_fn=None, log_writer=None, start_steps=None,
                     lr_schedule_values=None, wd_schedule_values=None, num_training_steps_per_epoch=None, update_freq=None,
@@ -66,6 +122,9 @@ def train_one_epoch(model: torch.nn.Module, criterion=None, data_loader: Iterabl
     start_steps = start_steps or 0
     optimizer = require_fused_optimizer(optimizer, core.arena, "train_one_epoch") or _default_optimizer(net)
     gs = getattr(model, "grad_sync", None)
+    if update_freq == 1:
+        return _train_one_epoch_graphed(model, net, data_loader, optimizer, gs, max_norm, start_steps, lr_schedule_values,
+                                        wd_schedule_values, num_training_steps_per_epoch)
     loss_sum = torch.zeros(1, device=dev)
     loss_acc = torch.zeros(1, device=dev)
     correct = torch.zeros(1, device=dev)
@@ -109,6 +168,38 @@ def train_one_epoch(model: torch.nn.Module, criterion=None, data_loader: Iterabl
     wds = [g["weight_decay"] for g in optimizer.param_groups if g["weight_decay"] > 0]
     return {"loss": loss_avg, "class_acc": (correct / max(seen, 1)).item(), "loss_scale": 1.0, "lr": max(lrs), "min_lr": min(lrs),
             "weight_decay": wds[0] if wds else None, "grad_norm": (gn_sum / max(1, n_updates)).item()}
+
+
+def _train_one_epoch_graphed(model, net, data_loader, optimizer, gs, max_norm, start_steps, lr_schedule_values, wd_schedule_values,
+                             num_training_steps_per_epoch):
+    """update_freq == 1 (the shipped stage-2 recipe): every loader batch is one whole update, run through Stage2Engine (CUDA-graph
+    replay).  Same schedule handling and return dict as the general loop above."""
+    eng = _stage2_engine(model, net, optimizer, gs)
+    eng.max_norm = float(max_norm) if max_norm else None
+    eng.stats.zero_()
+    dev = eng.core.arena.device
+    seen = n = 0
+    for data_iter_step, batch in enumerate(data_loader):
+        if num_training_steps_per_epoch is not None and data_iter_step >= num_training_steps_per_epoch:
+            continue                                                               # engine_for_finetuning.py:71-72
+        it = start_steps + data_iter_step
+        for group in optimizer.param_groups:                                       # engine_for_finetuning.py:76-81
+            if lr_schedule_values is not None:
+                group["lr"] = lr_schedule_values[min(it, len(lr_schedule_values) - 1)] * group.get("lr_scale", 1.0)
+            if wd_schedule_values is not None and group["weight_decay"] > 0:
+                group["weight_decay"] = wd_schedule_values[min(it, len(wd_schedule_values) - 1)]
+        eng.step(batch[0].to(dev, non_blocking=True), batch[1].to(dev, non_blocking=True), private_inputs=True)
+        seen += batch[0].shape[0]
+        n += 1
+    loss_sum, correct, gn_sum = eng.stats.tolist()
+    loss_avg = loss_sum / max(1, n)
+    if not math.isfinite(loss_avg):
+        print("Loss is {}, stopping training".format(loss_avg))
+        sys.exit(1)
+    lrs = [g["lr"] for g in optimizer.param_groups]
+    wds = [g["weight_decay"] for g in optimizer.param_groups if g["weight_decay"] > 0]
+    return {"loss": loss_avg, "class_acc": correct / max(seen, 1), "loss_scale": 1.0, "lr": max(lrs), "min_lr": min(lrs),
+            "weight_decay": wds[0] if wds else None, "grad_norm": gn_sum / max(1, n)}
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -32,7 +32,13 @@ class Stage3Engine:
     def __init__(self, student, teacher, cls_weight: torch.Tensor, cls_bias: torch.Tensor, text_features: torch.Tensor,
                  mask_ratio: float = 0.8, k: int = 2, clip_threshold: float = 0.5, src_ratio: float = 1.0, tgt_ratio: float = 1.0,
                  conf_weighted: bool = True, lr: float = 1e-4, weight_decay: float = 0.05, betas=(0.9, 0.999), grad_sync=None,
-                 optimizer: Optional[FusedAdamW] = None):
+                 optimizer: Optional[FusedAdamW] = None, use_graph: bool = False):
+        """use_graph: after two eager steps of a batch signature the whole step (the five forwards, both backwards, the gradient
+        exchange and AdamW: ~900 launches) is captured in a CUDA graph and replayed (engine.GraphReplay); nothing in it reads a
+        device value on the host, DropPath factors and optimizer scalars come from device memory."""
+        from .engine import GraphReplay
+        self.use_graph = use_graph
+        self.graphs = GraphReplay()
         self.student, self.teacher = student, teacher
         self.core = student.core()
         self.core.sync_shadow(force=True)
@@ -165,19 +171,33 @@ class Stage3Engine:
                          logits_masked=logits_masked, clip_probs=clip_probs, sel_mask=sel.bool(), pseudo=pseudo, msp=msp)
         return self.loss
 
-    def step(self, videos_s, labels_s, videos_t, videos_t_aug=None):
+    def _step_body_dev(self, videos_s, labels_s, videos_t, videos_t_aug):
         self.optimizer.zero_grad()
-        loss = self.forward_backward(videos_s, labels_s, videos_t, videos_t_aug)
+        self.forward_backward(videos_s, labels_s, videos_t, videos_t_aug)
         if self.nvls is not None:
-            self.optimizer.prepare_step(grad_scale=1.0 / self.nvls.world)
             if self.max_norm:
                 self.nvls.step_dev_clipped(self.max_norm)
             else:
                 self.nvls.step_dev()
-            return loss
-        scale = self.grad_sync.all_reduce(self.core.arena.grads) if self.grad_sync is not None else 1.0
-        self.optimizer.step(grad_scale=scale, max_norm=self.max_norm)
-        return loss
+            return
+        if self.grad_sync is not None:
+            self.grad_sync.all_reduce(self.core.arena.grads)
+        self.optimizer.step_dev(max_norm=self.max_norm)
+
+    def step(self, videos_s, labels_s, videos_t, videos_t_aug=None, private_inputs=False):
+        """One update.  private_inputs: the batch lives in fresh tensors every step (a loader), so a graph keeps its own inputs."""
+        world = self.nvls.world if self.nvls is not None else (self.grad_sync.world if self.grad_sync is not None else 1)
+        self.optimizer.prepare_step(grad_scale=1.0 / world)
+        if videos_t_aug is videos_t:
+            videos_t_aug = None
+        if not self.use_graph:
+            self._step_body_dev(videos_s, labels_s, videos_t, videos_t_aug)
+            return self.loss
+        key = (tuple(videos_s.shape), tuple(videos_t.shape), videos_t_aug is not None, labels_s.dtype, float(self.max_norm or 0.0),
+               bool(self.student.training), self.mask_ratio)
+        self.last = self.graphs.run(key, (videos_s, labels_s, videos_t, videos_t_aug), self._step_body_dev,
+                                    state_fn=lambda: self.last, private=private_inputs)
+        return self.loss
 
 
 def _engine_for(model, teacher_model, src_classifier, optimizer, mask_ratio, args):
@@ -199,7 +219,8 @@ def _engine_for(model, teacher_model, src_classifier, optimizer, mask_ratio, arg
                            src_ratio=float(getattr(args, "class_loss_src_ratio_pl", 1.0)),
                            tgt_ratio=float(getattr(args, "class_loss_tgt_ratio", 1.0)),
                            conf_weighted=bool(getattr(args, "conf_weighted_loss", True)), grad_sync=gs,
-                           optimizer=require_fused_optimizer(optimizer, student.core().arena, "train_one_epoch"))
+                           optimizer=require_fused_optimizer(optimizer, student.core().arena, "train_one_epoch"),
+                           use_graph=__import__("os").environ.get("UB_NO_GRAPH", "0") != "1")
         student.__dict__["_ub_stage3_engine"] = (teacher, cls, eng)
         return eng
     eng = held[2]
@@ -210,6 +231,7 @@ def _engine_for(model, teacher_model, src_classifier, optimizer, mask_ratio, arg
                 raise NotImplementedError("the fused NVLink step updates the plain [decay | no-decay] layout (UB_DDP_NVLS=0 otherwise)")
             eng.nvls.opt, new.gnorm_sq, new._sharded = new, eng.optimizer.gnorm_sq, eng.nvls
         eng.optimizer = new
+        eng.graphs.clear()                      # captured graphs hold the old optimizer's buffers
     eng.mask_ratio = mask_ratio
     return eng
 
@@ -262,7 +284,8 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, data_loader_t
             tb = next(it_target)
         videos_t = tb[0].to(dev, non_blocking=True)
         videos_t_aug = tb[1].to(dev, non_blocking=True) if dual else None
-        loss = eng.step(videos_s.to(dev, non_blocking=True), labels_s.to(dev, non_blocking=True), videos_t, videos_t_aug)
+        loss = eng.step(videos_s.to(dev, non_blocking=True), labels_s.to(dev, non_blocking=True), videos_t, videos_t_aug,
+                        private_inputs=True)
         scale = 1.0 / eng.grad_sync.world if eng.grad_sync is not None else 1.0
         acc += torch.cat([loss, eng.loss_s, eng.loss_t, opt.grad_norm(scale)])
         n += 1
