@@ -512,9 +512,11 @@ def test_stage2_graph_replay_matches_eager_steps():
     batches = [(torch.randn(6, *shape, generator=g).cuda(), torch.randint(0, scfg.num_classes, (6,), generator=g).cuda()) for _ in range(2)]
 
     class Args:
-        opt, lr, weight_decay, opt_betas, opt_eps = "adamw", 2e-3, 0.05, (0.9, 0.999), 1e-8
+        opt, lr, weight_decay, opt_betas, opt_eps = "adamw", 2e-4, 0.05, (0.9, 0.999), 1e-8
     runs = []
-    for use_graph in (True, False):
+    # a third, eager, run measures the run-to-run noise of the step itself (fp32 reduce-adds in the weight / LayerNorm gradients
+    # arrive in any order): the graph must agree with eager as well as eager agrees with itself
+    for use_graph in (True, False, False):
         vit = _build_vit(scfg, drop_path_rate=0.2)
         vit.load_state_dict(vsd, strict=True)
         vit = vit.cuda().train()
@@ -526,17 +528,20 @@ def test_stage2_graph_replay_matches_eager_steps():
         losses = []
         for s in range(7):
             for grp in opt.param_groups:                                          # a schedule: the graph must read lr from device memory
-                grp["lr"] = 2e-3 * (1 + s) / 7 * grp["lr_scale"]
+                grp["lr"] = 2e-4 * (1 + s) / 7 * grp["lr_scale"]
             losses.append(eng.step(*batches[s % 2]).clone())
         torch.cuda.synchronize()
         runs.append((torch.cat(losses).cpu(), eng.stats.cpu(), vit.core().arena.params.clone().cpu(), eng))
-    (l_g, st_g, p_g, eng_g), (l_e, st_e, p_e, _) = runs
+    (l_g, st_g, p_g, eng_g), (l_e, st_e, p_e, _), (l_e2, _, p_e2, _) = runs
     assert len(eng_g.graphs._graphs) == 2, "one graph per resident batch expected"
     assert int(eng_g.core.drop_path.step.item()) == 7, "capture must not consume a DropPath draw"
-    assert torch.allclose(l_g, l_e, rtol=2e-5, atol=0), (l_g, l_e)
+    noise_l, noise_p = ((l_e - l_e2).abs() / l_e.abs()).max().item(), rel_l2(p_e, p_e2)
+    d_l, d_p = ((l_g - l_e).abs() / l_e.abs()).max().item(), rel_l2(p_g, p_e)
+    print(f"stage-2 graph vs eager: loss {d_l:.2e} (eager vs eager {noise_l:.2e}), weights {d_p:.2e} (eager vs eager {noise_p:.2e})")
+    assert d_l <= max(2e-5, 4 * noise_l), (l_g, l_e)
     assert len(set(round(v, 5) for v in l_g.tolist())) >= 6, "replays did not see fresh DropPath factors / weights"
     assert torch.allclose(st_g, st_e, rtol=1e-4), (st_g, st_e)
-    assert rel_l2(p_g, p_e) < 1e-5
+    assert d_p <= max(1e-5, 4 * noise_p)
 
 
 def test_stage3_graph_replay_matches_eager_steps():
