@@ -546,7 +546,10 @@ def test_stage2_graph_replay_matches_eager_steps():
 
 def test_stage3_graph_replay_matches_eager_steps():
     """Stage3Engine(use_graph=True) against the eager engine: the five forwards, both backwards and AdamW of 6 updates (dual-view
-    target batch, DropPath 0.2 in every pass) replayed from the graph give the same losses and weights."""
+    target batch, DropPath 0.2 in every pass) replayed from the graph give the same losses and weights.  One step from identical
+    state is reproducible to fp32 reduction order (tools/stage3_determinism.py: gradients 3.5e-7 of their maximum, every discrete
+    decision identical); AdamW turns noise on a near-zero gradient into a full +-lr update of a weight the loss does not depend
+    on, so the learning rate is kept small, losses are compared tightly and weights against the distance they travelled."""
     from unite_b200.engine_stage3 import Stage3Engine
     fix, scfg, tcfg, ssd, tsd, *_ = _tiny()
     C, D = 12, scfg.embed_dim
@@ -563,7 +566,8 @@ def test_stage3_graph_replay_matches_eager_steps():
         student, teacher = build_student(scfg, drop_path_rate=0.2), build_teacher(tcfg)
         student.load_state_dict(ssd, strict=True)
         teacher.load_state_dict(tsd, strict=True)
-        eng = Stage3Engine(student.cuda().train(), teacher.cuda().eval(), cls_w, cls_b, text, mask_ratio=0.75, k=2, lr=1e-3, use_graph=use_graph)
+        eng = Stage3Engine(student.cuda().train(), teacher.cuda().eval(), cls_w, cls_b, text, mask_ratio=0.75, k=2, lr=2e-5, use_graph=use_graph)
+        p0 = eng.core.arena.params.clone().cpu()
         losses = []
         for s in range(6):
             eng.step(*batches[s % 2])
@@ -572,6 +576,9 @@ def test_stage3_graph_replay_matches_eager_steps():
         runs.append((torch.stack(losses).cpu(), eng.core.arena.params.clone().cpu(), eng))
     (l_g, p_g, eng_g), (l_e, p_e, _) = runs
     assert len(eng_g.graphs._graphs) == 2
-    assert torch.allclose(l_g, l_e, rtol=5e-5, atol=1e-7), (l_g, l_e)
-    assert rel_l2(p_g, p_e) < 1e-5
+    travelled, d_p = rel_l2(p_g, p0), rel_l2(p_g, p_e)
+    print(f"stage-3 graph vs eager: losses {(l_g - l_e).abs().max().item():.2e}, weights {d_p:.2e} of {travelled:.2e} travelled")
+    assert torch.allclose(l_g, l_e, rtol=3e-5, atol=1e-6), (l_g, l_e)
+    assert travelled > 3e-4 and d_p < 0.02 * travelled
+    assert len(set(round(v, 4) for v in l_g[:, 0].tolist())) >= 5, "replays did not see fresh inputs / DropPath factors"
     assert eng_g.last["sel_mask"].shape[0] == 4 and torch.isfinite(eng_g.last["logits_masked"]).all()
