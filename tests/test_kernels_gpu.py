@@ -42,6 +42,10 @@ def test_attention_forward_backward_cls(n_seq, S, H):
     m = _kc(); m.check_attention(n_seq, S, H); assert m.OK
 
 
+def test_teacher_attention_first_half_reference_and_its_redo_path():
+    m = _kc(); m.check_attention_tc_late_maximum(); assert m.OK
+
+
 def test_gemm_all_operand_majors_and_epilogues():
     g = importlib.import_module("gemm_check")
     ok = True

@@ -76,6 +76,34 @@ def check_attention(n_seq, S, H, time_it=False):
         print(f"   attn fwd {t*1e3:.0f} us ({fl/t/1e9:.0f} TF/s)   bwd {t2*1e3:.0f} us ({2.5*fl/t2/1e9:.0f} TF/s alg)")
 
 
+def check_attention_tc_late_maximum(n_seq=6, S=197, H=3):
+    """The register-resident teacher kernel (no LSE, S = 197) takes the maximum of the FIRST 96 keys as its softmax reference and
+    only redoes that half when a later key exceeds it by more than 2^60: rows whose maximum sits in the second half by a little, by
+    a lot (redo path), and rows dominated by the first half."""
+    g = torch.Generator(device=dev).manual_seed(1234)
+    qkv = (torch.randn(n_seq, S, 3, H, 64, device=dev, generator=g) * 0.7)
+    qkv[0, :, 1, :, :] *= 6.0                       # large scores everywhere
+    qkv[1, 120:, 1, :, :] *= 90.0                   # second-half keys far above the first half: the redo path (diff >> 60 / (scale log2 e))
+    qkv[2, :96, 1, :, :] *= 90.0                    # first-half keys dominate
+    qkv[3, 150, 1, :, :] *= 400.0                   # one huge late key
+    qkv[4, 196, 1, :, :] *= 400.0                   # ... the very last valid key (masked tail block)
+    qkv = qkv.bfloat16().view(n_seq * S, 3 * H * 64).contiguous()
+    o = torch.full((n_seq * S, H * 64), float("nan"), device=dev, dtype=torch.bfloat16)
+    scale = 0.125
+    ops.attn_fwd(qkv, o, None, n_seq, S, H, scale)
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(n_seq, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * scale
+    oref = s.softmax(-1) @ v
+    late = ((s[..., 96:].max(-1).values - s[..., :96].max(-1).values) * 1.4427 > 60).float().mean().item()
+    print(f"   rows on the redo path: {100 * late:.1f} %")
+    global OK
+    OK &= late > 0.05
+    got = o.view(n_seq, S, H, 64).permute(0, 2, 1, 3)
+    OK &= bool(torch.isfinite(got.float()).all())
+    report(f"attn_fwd_tc late maximum S={S} H={H}", got, oref, 8e-3)
+
+
 def check_ln(rows, D):
     g = torch.Generator(device=dev).manual_seed(D + rows)
     x = torch.randn(rows, D, device=dev, generator=g) * 2 + 0.3
@@ -225,6 +253,7 @@ if __name__ == "__main__":
     check_attention(3, 320, 12)
     check_attention(2, 64, 2)
     check_attention(1, 1568, 4)
+    check_attention_tc_late_maximum()
     check_attention(256, 197, 12, time_it=True)
     check_attention(32, 320, 12, time_it=True)
     print("ALL OK" if OK else "SOME FAILED")

@@ -30,6 +30,15 @@ struct AttnTcParams {
   uint32_t idesc_s, idesc_o, idesc_r;
 };
 constexpr int ONES_BYTES = 16 * 4 * 128;   // [16 rows (N)] x [256 keys (K)] bf16, K-major: 4 k-blocks of 16 x 128 B
+// register-resident kernels (NKT > 0): the first ATC_NH0 32-key blocks of a score row are turned into P while the rest is still
+// being read; their P lives in the tile's spare columns [NKT, NKT + 16 * ATC_NH0) instead of over the scores
+#ifndef UB_ATTN_TC_ONE_LOAD
+constexpr int ATC_NH0(int nkt) { return (nkt / 32) / 2; }
+#else
+constexpr int ATC_NH0(int) { return 0; }
+#endif
+// TMEM column (within the tile) of the bf16 P operand of key step k (16 keys = 8 columns)
+UB_DEVINL constexpr uint32_t atc_p_col(int nkt, int k) { return nkt > 0 && k < 2 * ATC_NH0(nkt) ? (uint32_t)(nkt + k * 8) : (uint32_t)(k * 8); }
 
 // NKT == 0: generic (runtime NK, two TMEM passes over S, 10 warps).
 // NKT  > 0: NK == NKT at compile time; each softmax thread keeps its whole score row (NKT fp32) in REGISTERS, so S is read
@@ -133,11 +142,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint64_t vd = umma_desc_mnmajor_sw128(sV, 8192);
           const int ksteps = (NKT ? NKT : p.NK) >> 4;
           for (int k = 0; k < ksteps; ++k)
-            umma_bf16_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + k * 8, vd + (uint64_t)(k * 128), p.idesc_o, k > 0 ? 1u : 0u);
+            umma_bf16_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + atc_p_col(NKT, k), vd + (uint64_t)(k * 128), p.idesc_o, k > 0 ? 1u : 0u);
           // row sums of the bf16 P actually used above:  P (128 x NK) x ones (NK x 16)
           const uint64_t od = umma_desc_kmajor_sw128(sOnes);
           for (int k = 0; k < ksteps; ++k)
-            umma_bf16_ts(tmem_base + t * 256 + 192, tmem_base + t * 256 + k * 8, od + (uint64_t)((k >> 2) * 128 + (k & 3) * 2), p.idesc_r,
+            umma_bf16_ts(tmem_base + t * 256 + 192, tmem_base + t * 256 + atc_p_col(NKT, k), od + (uint64_t)((k >> 2) * 128 + (k & 3) * 2), p.idesc_r,
                          k > 0 ? 1u : 0u);
           umma_commit(&o_full[t]);
           if (t == t_hi - 1) umma_commit(&kv_empty[st]);   // every MMA of this stream has read the item's smem
@@ -166,9 +175,96 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(&s_full[t], it & 1);
         tc_fence_after();
         if constexpr (NKT > 0) {
-          // ---- single pass: the whole score row in registers (S > NKT - 16 by construction: only the last 16 need masks)
+          // ---- single pass: every score is read from TMEM once (S > NKT - 16 by construction: only the last 16 need masks).
+          // The row is fetched in two halves: the second half is in flight on the TMEM read port while the first half is in
+          // the exponentials, which takes the load time of half a row out of the tile's QK^T -> softmax -> PV dependency chain
+          // (that chain, not a throughput limit, is what bounds this kernel: profiles/ncu_attn_r01b_pingpong.txt).  The softmax
+          // reference is the maximum of the FIRST half: O / l is invariant under the common factor, so the result is exact; only
+          // if the second half exceeds it by more than 2^60 are the first half's exponentials redone against the true maximum.
+          // P of the first half goes to the 48 spare columns [208, 256) of the tile, so its scores stay intact in TMEM for that
+          // redo and their registers are free while the second half is processed.
           constexpr int NFULL = NKT / 32, TAIL = NKT % 32;
+          constexpr int NH0 = ATC_NH0(NKT);                 // 32-column loads of the first half
           static_assert(TAIL == 0 || TAIL == 16, "NKT must be a multiple of 16");
+          static_assert(NH0 * 32 <= NKT - 16 && NKT + NH0 * 16 <= 256, "first half: unmasked, and its P must fit the spare columns");
+#ifndef UB_ATTN_TC_ONE_LOAD
+          float mb1;
+          auto exp32 = [&](const uint32_t (&v)[32], int c) {         // keys [32 c, 32 c + 32) -> bf16 P
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int k0 = c * 32 + 2 * i;
+              float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sl2, -mb1));
+              float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -mb1));
+              if (k0 >= NKT - 16) {
+                if (k0 >= S) p0 = 0.f;
+                if (k0 + 1 >= S) p1 = 0.f;
+              }
+              pk[i] = pack_bf16x2(p0, p1);
+            }
+            tmem_st_32x16(t_row + (c < NH0 ? NKT + c * 16 : c * 16), pk);
+          };
+          uint32_t s0[NH0][32], s1[NFULL - NH0][32], s1t[16];
+#pragma unroll
+          for (int c = 0; c < NH0; ++c) tmem_ld_32x32(t_row + c * 32, s0[c]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = NH0; c < NFULL; ++c) tmem_ld_32x32(t_row + c * 32, s1[c - NH0]);     // in flight during the exponentials below
+          if constexpr (TAIL) tmem_ld_32x16(t_row + NFULL * 32, s1t);
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 0; c < NH0; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(s0[c][i]));
+          const float m0 = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          mb1 = m0 * sl2;
+          // ping-pong: the exp phases of the two warpgroups alternate (each gets the full MUFU rate while the other one
+          // waits on / feeds the tensor pipe).  Named barriers 2 (A's turn) and 3 (B's turn), 256 threads each.
+          if (t == 0) asm volatile("bar.sync 2, 256;" ::: "memory"); else asm volatile("bar.sync 3, 256;" ::: "memory");
+#pragma unroll
+          for (int c = 0; c < NH0; ++c) exp32(s0[c], c);
+          tmem_ld_wait();                                   // the second half has landed
+          float n4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = NH0; c < NFULL; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (c * 32 + i < NKT - 16 || c * 32 + i < S) n4[i & 3] = fmaxf(n4[i & 3], __uint_as_float(s1[c - NH0][i]));
+            }
+          if constexpr (TAIL) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (NFULL * 32 + i < S) n4[i & 3] = fmaxf(n4[i & 3], __uint_as_float(s1t[i]));
+          }
+          const float m1 = fmaxf(fmaxf(n4[0], n4[1]), fmaxf(n4[2], n4[3]));
+          if (__any_sync(0xffffffffu, (m1 - m0) * sl2 > 60.0f)) {
+            // rare: redo the first half against the true maximum, one 32-key block at a time from its intact scores
+            mb1 = fmaxf(m0, m1) * sl2;
+#pragma unroll 1
+            for (int c = 0; c < NH0; ++c) {
+              uint32_t r[32], pk[16];
+              tmem_ld_32x32(t_row + c * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                pk[i] = pack_bf16x2(fast_exp2(fmaf(__uint_as_float(r[2 * i]), sl2, -mb1)), fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mb1)));
+              tmem_st_32x16(t_row + NKT + c * 16, pk);
+            }
+          }
+#pragma unroll
+          for (int c = NH0; c < NFULL; ++c) exp32(s1[c - NH0], c);
+          if constexpr (TAIL) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int k0 = NFULL * 32 + 2 * i;
+              const float p0 = (k0 < S) ? fast_exp2(fmaf(__uint_as_float(s1t[2 * i]), sl2, -mb1)) : 0.f;
+              const float p1 = (k0 + 1 < S) ? fast_exp2(fmaf(__uint_as_float(s1t[2 * i + 1]), sl2, -mb1)) : 0.f;
+              pk[i] = pack_bf16x2(p0, p1);
+            }
+            tmem_st_32x8(t_row + NFULL * 16, pk);
+          }
+#else
           uint32_t sv[NKT];
 #pragma unroll
           for (int c = 0; c < NFULL; ++c) tmem_ld_32x32(t_row + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
@@ -181,8 +277,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int i = NKT - 16; i < NKT; ++i)
             if (i < S) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sv[i]));
           const float mb1 = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sl2;
-          // ping-pong: the exp phases of the two warpgroups alternate (each gets the full MUFU rate while the other one
-          // waits on / feeds the tensor pipe).  Named barriers 2 (A's turn) and 3 (B's turn), 256 threads each.
           if (t == 0) asm volatile("bar.sync 2, 256;" ::: "memory"); else asm volatile("bar.sync 3, 256;" ::: "memory");
 #pragma unroll
           for (int c = 0; c < NKT / 32; ++c) {
@@ -211,6 +305,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
             tmem_st_32x8(t_row + NFULL * 16, pk);
           }
+#endif
           if (t == 0) asm volatile("bar.arrive 3, 256;" ::: "memory"); else asm volatile("bar.arrive 2, 256;" ::: "memory");
         } else {
         // ---- pass 1: row maximum over the valid keys (only the chunk that straddles S pays for masking)
@@ -283,15 +378,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         __syncwarp();
         mbar_wait(&o_full[t], it & 1);
         tc_fence_after();
-        uint32_t rsum;
+        // all of O (64 fp32 per row) and the row sum are taken out of TMEM first, so the tile's columns go back to the MMA warp
+        // (next item's Q K^T) before the normalise / pack / staging work instead of after it
+        uint32_t rsum, r0[32], r1[32];
         tmem_ld_32x1(t_row + 192, rsum);
+        tmem_ld_32x32(t_row + 128, r0);
+        tmem_ld_32x32(t_row + 160, r1);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);            // S / P / O columns of this tile may be overwritten by the next item
         const float inv = 1.0f / __uint_as_float(rsum);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_row + 128 + hh * 32, r);
-          tmem_ld_wait();
+          const uint32_t* r = hh ? r1 : r0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t a = stg_a + (uint32_t)lane * 128u + ((((uint32_t)(hh * 4 + j)) ^ (uint32_t)(lane & 7)) << 4);
@@ -303,15 +403,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                          : "memory");
           }
         }
-        tc_fence_before();
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&s_free[t]);            // S / P / O columns of this tile may be overwritten by the next item
-          if (row0 < S) {
-            tma_store_3d(&tmO, stg, h * 64, row0, seq);
-            tma_store_commit();
-          }
+        if (lane == 0 && row0 < S) {
+          tma_store_3d(&tmO, stg, h * 64, row0, seq);
+          tma_store_commit();
         }
       }
       if (lane == 0) tma_store_wait_read<0>();
