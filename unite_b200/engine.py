@@ -204,6 +204,9 @@ class FusedAdamW:
             g.update({k: v for k, v in saved.items() if k != "params"})
 
 
+_ASYNC_ZERO = os.environ.get("UB_ASYNC_ZERO", "1") != "0"
+
+
 class GraphReplay:
     """CUDA-graph plumbing shared by the stage-2 and stage-3 engines (Stage1Engine.step carries the same logic inline): the first
     two steps of an input signature run eagerly (lazy attribute setting, workspace allocation, NCCL initialisation), then the
@@ -336,9 +339,10 @@ class Stage1Engine:
         return P - int(P * self.mask_ratio)                      # run_stage1.py:380
 
     def forward_backward(self, videos: torch.Tensor, q: torch.Tensor, dp: Optional[torch.Tensor] = None,
-                         attn_override: Optional[torch.Tensor] = None, clip_loss_type: Optional[str] = None):
+                         attn_override: Optional[torch.Tensor] = None, clip_loss_type: Optional[str] = None, grads_ready=None):
         """Everything up to (not including) the optimizer.  videos fp32 [B,3,T,H,W] on the device; q fp32 [B*T',HW]
-        Exp(1) noise for the mask sampler.  Returns the device loss tensor [1]."""
+        Exp(1) noise for the mask sampler.  Returns the device loss tensor [1].
+        grads_ready: event after which the gradient arena may be written (its fill runs on a side stream, _step_body_dev)."""
         core, teacher = self.core, self.teacher
         B = videos.shape[0]
         patches = None
@@ -390,6 +394,8 @@ class Stage1Engine:
             # shipped config: the loss and its gradient are fused into the decoder-tail kernels
             _, x_clip, state = core.run_forward(videos, vis_idx[0], patches_s, dp, True, True,
                                                 targets=targets, loss_acc=self.loss, loss_clips=loss_clips)
+            if grads_ready is not None:
+                torch.cuda.current_stream().wait_event(grads_ready)
             core.run_backward(state, targets=targets, grad_sync=self._backward_hook())
         else:
             # run_stage1.py:403-408,432-433 (nn.MSELoss / nn.SmoothL1Loss / nn.L1Loss, mean reduction): loss value and
@@ -416,6 +422,8 @@ class Stage1Engine:
                 g = d.sign() / n                                                   # sign(0) = 0 on the rows outside the slice
             else:
                 raise NotImplementedError(f"clip_loss_type={kind!r} (run_stage1.py:430-435 raises for anything else too)")
+            if grads_ready is not None:
+                torch.cuda.current_stream().wait_event(grads_ready)
             core.run_backward(state, g_clip=g, grad_sync=self._backward_hook())
         self.last = dict(attn=attn, mask=mask.view(B, Tp * P).bool(), vis_idx=vis_idx[0], targets=targets, outputs=x_clip)
         return self.loss
@@ -443,8 +451,22 @@ class Stage1Engine:
         return lo, hi
 
     def _step_body_dev(self, videos, q):
-        self.optimizer.zero_grad()
-        self.forward_backward(videos, q, None)
+        # The 352 MB fill of the gradient arena runs on a side stream beside the teacher's forward (an HBM-write-bound fill next to
+        # L2 / tensor-bound GEMMs) and is joined right before the first gradient is written; inside a CUDA graph this is a fork /
+        # join of two branches.  UB_ASYNC_ZERO=0: in line, ahead of the step.
+        zeroed = None
+        if _ASYNC_ZERO and self.core.arena.device.type == "cuda":
+            cur = torch.cuda.current_stream()
+            if getattr(self, "_zero_stream", None) is None:
+                self._zero_stream = torch.cuda.Stream(device=self.core.arena.device)
+            self._zero_stream.wait_stream(cur)
+            with torch.cuda.stream(self._zero_stream):
+                self.optimizer.zero_grad()
+                zeroed = torch.cuda.Event()
+                zeroed.record()
+        else:
+            self.optimizer.zero_grad()
+        self.forward_backward(videos, q, None, grads_ready=zeroed)
         if self.nvls is not None:
             if self.max_norm:
                 self.nvls.step_dev_clipped(self.max_norm)

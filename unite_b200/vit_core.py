@@ -51,11 +51,14 @@ _FUSE_QKV_BIAS = os.environ.get("UB_FUSE_QKV_BIAS", "1") == "1"
 # of the block's backward (ub_gemm_wgrad_multi) instead of four: one prologue / pipeline fill / drain and one wave quantisation
 # on the 74 CTA pairs (108 pair tiles x split-K 2 = 216 items = 2.9 waves) instead of four.  UB_MULTI_WGRAD=0: separate launches.
 _MULTI_WGRAD = os.environ.get("UB_MULTI_WGRAD", "1") == "1"
+_FORCE_WGRAD_SPLIT = int(os.environ.get("UB_WGRAD_SPLIT", "0"))      # experiments: fixed split-K factor of the multi-problem launch
 
 
 def _multi_splits(problems, units):
     """split-K factor for a multi-problem weight-gradient launch: the SMALLEST one that fills the waves of `units` CTA pairs to
     >= 93 % (every extra split is another fp32 reduce-add pass over the weight-gradient tiles), >= 32 k-blocks per item."""
+    if _FORCE_WGRAD_SPLIT > 0:
+        return _FORCE_WGRAD_SPLIT
     tiles = sum(((gw.shape[0] + 255) // 256) * ((gw.shape[1] + 255) // 256) for _, _, gw in problems)
     kb = (problems[0][0].shape[0] + 63) // 64
     best, best_eff = 1, 0.0
