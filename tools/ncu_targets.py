@@ -1,6 +1,7 @@
 """Small launch sets for `ncu --set full` captures of the kernels the round-1 verdict asked evidence for.
 
     python tools/ncu_targets.py gemm      # student shapes 10240x768x3072 (fc2 fwd: fp32 out + residual) and 10240x2304x768 (qkv fwd)
+    python tools/ncu_targets.py teacher_attn   # the teacher's 197-token forward, 256 frames x 12 heads
     python tools/ncu_targets.py attn      # long-sequence attention fwd + two-pass bwd, n_seq=4 S=1568 H=12
     python tools/ncu_targets.py membound  # patchify, LN fwd/bwd, dec_tail, gather, AdamW at the step's shapes
 Each mode warms up once, then runs the launches of interest between cudaProfilerStart/Stop (use --profile-from-start off).
@@ -40,6 +41,11 @@ if mode == "gemm":
         ops.gemm(a1, w1, o1, bias=b1, residual=res)        # fc2 forward: 10240 x 768 x 3072
         ops.gemm(a2, w2, o2, bias=b2)                      # qkv forward: 10240 x 2304 x 768
     profiled(run)
+elif mode == "teacher_attn":
+    n_seq, S, H = 256, 197, 12                              # one teacher layer of the B = 32 step: 3072 (frame, head) items
+    qkv = (torch.randn(n_seq * S, 3 * H * 64, device=dev, generator=g) * 0.7).bfloat16()
+    o = torch.empty(n_seq * S, H * 64, device=dev, dtype=torch.bfloat16)
+    profiled(lambda: ops.attn_fwd(qkv, o, None, n_seq, S, H, 0.125))
 elif mode == "attn":
     n_seq, S, H = 4, 1568, 12
     qkv = (torch.randn(n_seq * S, 3 * H * 64, device=dev, generator=g) * 0.7).bfloat16()
