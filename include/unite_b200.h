@@ -39,7 +39,7 @@ UB_API int ub_set_sm_limit(int n);
  *   student  modeling_finetune.py:108 (qkv), :117 (proj), :67-71 (fc1/fc2), :174 (PatchEmbed.proj),
  *            modeling_adaptation.py:204 (Linear_Decoder.head), and their autograd backward (dgrad / wgrad).
  * ---------------------------------------------------------------------------------------------- */
-enum { UB_ACT_NONE = 0, UB_ACT_QUICKGELU = 1, UB_ACT_GELU = 2, UB_ACT_DGELU = 3 };
+enum { UB_ACT_NONE = 0, UB_ACT_QUICKGELU = 1, UB_ACT_GELU = 2, UB_ACT_DGELU = 3, UB_ACT_DOT_AUX = 4 };
 
 typedef struct ub_gemm_epilogue {
   const float* bias;      /* [N] added to the accumulator, or NULL                                         */
@@ -87,6 +87,14 @@ typedef struct ub_gemm_epilogue {
    * Python front end passes a workspace only on request (ops.gemm(stream_k=True) / UB_GEMM_SK=1). */
   void* sk_workspace;
   int64_t sk_workspace_bytes;
+  /* UB_ACT_DOT_AUX (bf16 out, N a multiple of 64): C = acc as usual, and in the same pass
+   *   dot_out[((m / dot_seq_len) * (N / 64) + n / 64) * dot_seq_len + m % dot_seq_len] = sum over the 64 columns of head n / 64 of
+   *   bf16(C[m, n]) * aux_in[m, n]
+   * With C = dO (the attention-output gradient, produced by the proj dgrad GEMM) and aux_in = O this is D = rowsum(dO o O) in the
+   * [n_seq, H, S] layout ub_attn_bwd wants (modeling_finetune.py:110-117 under autograd): the separate pass over O and dO goes away. */
+  float* dot_out;
+  int32_t dot_seq_len;
+  int32_t reserved0;
 } ub_gemm_epilogue;
 
 /* bytes of ub_gemm_epilogue.sk_workspace that cover every shape on this device */
@@ -135,7 +143,9 @@ UB_API int ub_attn_fwd(const void* qkv, void* o, float* lse /* may be NULL */, i
                        void* stream);
 /* dbias (may be NULL): fp32 [3*H*64], += the column sums over all rows of the dq and dv thirds of dqkv — the q_bias / v_bias
  * gradients of modeling_finetune.py:104-108 (the key third has no bias and is left untouched) — accumulated by the kernels as they
- * store dqkv, which saves the separate pass over it. */
+ * store dqkv, which saves the separate pass over it.
+ * o may be NULL when D_ws already holds D = rowsum(dO o O) in its [n_seq, H, S] layout (written by the GEMM that produced dO:
+ * ub_gemm_epilogue.dot_out); otherwise D is computed here from o and d_o first. */
 UB_API int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* D_ws, void* dqkv, float* dbias,
                        int n_seq, int S, int H, float scale, void* stream);
 UB_API int ub_cls_attn(const void* qkv, float* out, int n_seq, int S, int H, float scale, void* stream);

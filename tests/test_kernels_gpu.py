@@ -46,6 +46,11 @@ def test_teacher_attention_first_half_reference_and_its_redo_path():
     m = _kc(); m.check_attention_tc_late_maximum(); assert m.OK
 
 
+@pytest.mark.parametrize("B,N,H", [(5, 320, 12), (3, 197, 4), (2, 1568, 12), (1, 40, 2)])
+def test_gemm_epilogue_leaves_rowsum_dO_O_for_the_attention_backward(B, N, H):
+    m = _kc(); m.check_gemm_dot_aux(B, N, H); assert m.OK
+
+
 def test_gemm_all_operand_majors_and_epilogues():
     g = importlib.import_module("gemm_check")
     ok = True

@@ -104,6 +104,32 @@ def check_attention_tc_late_maximum(n_seq=6, S=197, H=3):
     report(f"attn_fwd_tc late maximum S={S} H={H}", got, oref, 8e-3)
 
 
+def check_gemm_dot_aux(B=5, N=320, H=12, time_it=False):
+    """ub_gemm_epilogue.dot_out: the proj dgrad GEMM that writes dO also leaves D = rowsum(dO o O) per (token, head) in ub_attn_bwd's
+    [n_seq, H, S] layout; dO must be bit-identical to the plain GEMM's, D within fp32 summation order of the torch value."""
+    global OK
+    g = torch.Generator(device=dev).manual_seed(B * 7 + N)
+    M, D = B * N, H * 64
+    dy = (torch.randn(M, D, device=dev, generator=g) * 0.3).bfloat16()
+    w = (torch.randn(D, D, device=dev, generator=g) * D ** -0.5).bfloat16()          # [out, in] as stored; dgrad contracts over `out`
+    o = torch.randn(M, D, device=dev, generator=g).bfloat16()
+    d_o_plain = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    ops.gemm(dy, w, d_o_plain, b_t=True)
+    d_o = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    dws = torch.full((B, H, N), float("nan"), device=dev)
+    ops.gemm(dy, w, d_o, b_t=True, act=ops.UB_ACT_DOT_AUX, aux_in=o, dot_out=dws, dot_seq_len=N)
+    torch.cuda.synchronize()
+    same = torch.equal(d_o, d_o_plain)
+    OK &= same
+    print(f"gemm dot_aux dO bit-identical to the plain GEMM: {same}")
+    want = (d_o.float() * o.float()).view(B, N, H, 64).sum(-1).permute(0, 2, 1)
+    report(f"gemm dot_aux D B={B} N={N} H={H}", dws, want, 2e-6)
+    if time_it:
+        t0 = timeit(lambda: ops.gemm(dy, w, d_o_plain, b_t=True))
+        t1 = timeit(lambda: ops.gemm(dy, w, d_o, b_t=True, act=ops.UB_ACT_DOT_AUX, aux_in=o, dot_out=dws, dot_seq_len=N))
+        print(f"   proj dgrad {M}x{D}x{D}: plain {t0*1e3:.1f} us, with D {t1*1e3:.1f} us")
+
+
 def check_ln(rows, D):
     g = torch.Generator(device=dev).manual_seed(D + rows)
     x = torch.randn(rows, D, device=dev, generator=g) * 2 + 0.3
@@ -254,6 +280,8 @@ if __name__ == "__main__":
     check_attention(2, 64, 2)
     check_attention(1, 1568, 4)
     check_attention_tc_late_maximum()
+    check_gemm_dot_aux(5, 320, 12); check_gemm_dot_aux(3, 197, 4); check_gemm_dot_aux(2, 1568, 12)
+    check_gemm_dot_aux(32, 320, 12, time_it=True)
     check_attention(256, 197, 12, time_it=True)
     check_attention(32, 320, 12, time_it=True)
     print("ALL OK" if OK else "SOME FAILED")

@@ -10,7 +10,7 @@ import os
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
                          "libunite_b200%s.so" % ("_" + os.environ["UB_LIB_VARIANT"] if os.environ.get("UB_LIB_VARIANT") else ""))
 
-UB_ACT_NONE, UB_ACT_QUICKGELU, UB_ACT_GELU, UB_ACT_DGELU = 0, 1, 2, 3
+UB_ACT_NONE, UB_ACT_QUICKGELU, UB_ACT_GELU, UB_ACT_DGELU, UB_ACT_DOT_AUX = 0, 1, 2, 3, 4
 
 
 class GemmEpilogue(C.Structure):
@@ -44,6 +44,9 @@ class GemmEpilogue(C.Structure):
         ("group_bias", C.c_int32),
         ("sk_workspace", C.c_void_p),
         ("sk_workspace_bytes", C.c_int64),
+        ("dot_out", C.c_void_p),
+        ("dot_seq_len", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 

@@ -603,13 +603,15 @@ extern "C" int ub_attn_fwd(const void* qkv, void* o, float* lse, int n_seq, int 
 
 extern "C" int ub_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* D_ws, void* dqkv, float* dbias,
                            int n_seq, int S, int H, float scale, void* stream) {
-  UB_REQUIRE(qkv && o && d_o && lse && D_ws && dqkv, "attn_bwd: null pointer");
+  UB_REQUIRE(qkv && d_o && lse && D_ws && dqkv, "attn_bwd: null pointer");
   UB_REQUIRE(n_seq > 0 && S > 0 && H > 0, "attn_bwd: bad shape n_seq=%d S=%d H=%d", n_seq, S, H);
   cudaStream_t st = (cudaStream_t)stream;
   const int n_rows = n_seq * S;
   const long n_chunks = (long)n_rows * H * 8;
-  UB_LAUNCH(attn_bwd_prep_kernel, (unsigned)((n_chunks + 255) / 256), 256, 0, st, (const bf16*)o, (const bf16*)d_o, D_ws, n_chunks, S, H);
-  if (check_launch("attn_bwd_prep_kernel")) return 1;
+  if (o != nullptr) {        // o == NULL: D_ws already holds rowsum(dO o O) (the GEMM that produced dO wrote it: ub_gemm_epilogue.dot_out)
+    UB_LAUNCH(attn_bwd_prep_kernel, (unsigned)((n_chunks + 255) / 256), 256, 0, st, (const bf16*)o, (const bf16*)d_o, D_ws, n_chunks, S, H);
+    if (check_launch("attn_bwd_prep_kernel")) return 1;
+  }
   // short sequences (the student's <= 320 visible tokens): single-pass tcgen05 / TMEM kernel
   static int use_tc = -1;
   if (use_tc < 0) {

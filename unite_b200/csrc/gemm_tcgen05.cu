@@ -60,6 +60,8 @@ struct GemmParams {
   float ln_inv_d, ln_eps;
   float* stats_out;         // EPI 3: row (sum, sumsq) of the fp16 output
   float* colsum_out;        // EPI 2: += column sums of the values written to C (the bias gradient of the Linear that produced aux)
+  float* dot_out;           // EPI 2 with act == UB_ACT_DOT_AUX: per (row, 64-column head) dot product of the bf16 output with aux
+  int dot_seq_len;
   // grouped GEMM (ub_gemm_epilogue.group_*): work item with first C row m0 belongs to group g = m0 / group_rows
   int group_rows;           // 0 = ungrouped
   int a_k_off, a_m_off;     // A coordinates: k += g * a_k_off, m -= g * a_m_off
@@ -544,6 +546,7 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
           mbar_wait(&rb[b], NBUF == 3 ? ((cc / 3u) & 1u) : ((cc >> 1) & 1u));
         }
         // ---- accumulators -> registers -> epilogue math -> staging slab (row per lane, 128 B per row)
+        float dsum = 0.0f;        // UB_ACT_DOT_AUX: this lane's row of the slab (64 columns = one head) dotted with aux
 #pragma unroll
         for (int h = 0; h < CW / 32; ++h) {
           uint32_t r[32];
@@ -610,7 +613,24 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
               }
             }
           }
-          if (EPI == 2) {
+          if (EPI == 2 && p.act == UB_ACT_DOT_AUX) {
+            // dot product of the bf16-rounded output with aux (the values the consumer of C and of dot_out will see)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w)
+                           : "r"(slab0_a + ((uint32_t)b << 12) + rowoff + ((((uint32_t)(h * 4 + j)) ^ sw) << 4)));
+              const uint32_t ax[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 o2 = unpack_bf16x2(ax[q]);
+                const float2 c2 = unpack_bf16x2(pack_bf16x2(v[8 * j + 2 * q], v[8 * j + 2 * q + 1]));
+                dsum = fmaf(c2.x, o2.x, dsum);
+                dsum = fmaf(c2.y, o2.y, dsum);
+              }
+            }
+          } else if (EPI == 2) {
             // multiply by gelu'(pre-activation): bf16 slab row of this lane, chunks h*4 .. h*4+3
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -694,6 +714,13 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
                            "r"(pack_bf16x2(v[8 * j + 6], v[8 * j + 7]))
                            : "memory");
             }
+          }
+        }
+        if (EPI == 2 && p.act == UB_ACT_DOT_AUX) {
+          const int row = row0 + lane;
+          if (row < p.M && col0 < p.N) {
+            const int seq = row / p.dot_seq_len, r = row - seq * p.dot_seq_len;
+            p.dot_out[((size_t)seq * (p.N >> 6) + (col0 >> 6)) * p.dot_seq_len + r] = dsum;
           }
         }
         // ---- hand the slab to the TMA engine
@@ -990,6 +1017,10 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   UB_REQUIRE(!ep.accumulate || ep.out_fp32, "gemm: accumulate needs fp32 output");
   UB_REQUIRE(ep.row_scale == nullptr || ep.rows_per_scale > 0, "gemm: rows_per_scale must be > 0");
   UB_REQUIRE(ep.act != UB_ACT_DGELU || ep.aux_in != nullptr, "gemm: DGELU needs aux_in");
+  UB_REQUIRE(ep.act != UB_ACT_DOT_AUX || (ep.aux_in != nullptr && ep.dot_out != nullptr && ep.dot_seq_len > 0 && !ep.out_fp32 && N % 64 == 0 &&
+                                          M % ep.dot_seq_len == 0 && ep.residual == nullptr && !ep.accumulate && ep.row_scale == nullptr &&
+                                          ep.colsum_out == nullptr && ep.group_rows == 0),
+             "gemm: UB_ACT_DOT_AUX needs aux_in, dot_out, dot_seq_len dividing M, a bf16 output with N %% 64 == 0 and no other epilogue option");
   UB_REQUIRE(!(ep.act == UB_ACT_DGELU && ep.residual != nullptr), "gemm: DGELU with a residual is not supported");
   UB_REQUIRE(ep.residual == nullptr || ep.out_fp32 || ep.residual_f16, "gemm: the residual epilogue writes fp32 (or fp16 with residual_f16)");
   UB_REQUIRE(!ep.residual_f16 || (ep.residual != nullptr && !ep.out_fp32), "gemm: residual_f16 needs a residual and a 2-byte (fp16) output");
@@ -1064,7 +1095,7 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   if (ep.tile_ctas == 2 && bn == 256 && M > BM) ncta = 2;
   if (ep.tile_ctas == 4 && bn == 256 && M >= 4 * BM && units4 > 0) ncta = 4;
 
-  const int epi = ep.residual != nullptr ? (ep.residual_f16 ? 3 : 1) : (ep.act == UB_ACT_DGELU ? 2 : 0);
+  const int epi = ep.residual != nullptr ? (ep.residual_f16 ? 3 : 1) : ((ep.act == UB_ACT_DGELU || ep.act == UB_ACT_DOT_AUX) ? 2 : 0);
   const bool out32 = ep.out_fp32 != 0;
   GemmMaps m;
   memset(&m, 0, sizeof(m));
@@ -1098,6 +1129,7 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   p.ln_stats = ep.ln_stats; p.ln_c = ep.ln_c; p.ln_inv_d = ep.ln_inv_d; p.ln_eps = ep.ln_eps;
   p.stats_out = ep.stats_out;
   p.colsum_out = ep.colsum_out;
+  p.dot_out = ep.dot_out; p.dot_seq_len = ep.dot_seq_len;
   p.group_rows = ep.group_rows; p.a_k_off = ep.group_a_k; p.a_m_off = ep.group_a_m;
   p.b_k_off = ep.group_b_k; p.b_n_off = ep.group_b_n; p.bias_off = ep.group_bias;
   const long total_work = (long)((M + BM * ncta - 1) / (BM * ncta)) * ((N + bn - 1) / bn) * split_k;

@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _cabi
-from ._cabi import lib, check, GemmEpilogue, UB_ACT_NONE, UB_ACT_QUICKGELU, UB_ACT_GELU, UB_ACT_DGELU  # noqa: F401
+from ._cabi import lib, check, GemmEpilogue, UB_ACT_NONE, UB_ACT_QUICKGELU, UB_ACT_GELU, UB_ACT_DGELU, UB_ACT_DOT_AUX  # noqa: F401
 
 BF16, F32, I32, U8 = torch.bfloat16, torch.float32, torch.int32, torch.uint8
 F16 = torch.float16
@@ -91,13 +91,16 @@ def _sk_workspace(ep):
 @_instrument("gemm", 1)
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=False, bias=None, residual=None,
          row_scale=None, rows_per_scale=0, act=UB_ACT_NONE, aux_in=None, aux_out=None, accumulate=False, split_k=1, tile_ctas=0,
-         max_ctas=0, ln_stats=None, ln_c=None, ln_eps=0.0, stats_out=None, colsum_out=None, group=None, stream_k=None):
+         max_ctas=0, ln_stats=None, ln_c=None, ln_eps=0.0, stats_out=None, colsum_out=None, group=None, stream_k=None, dot_out=None, dot_seq_len=0):
     """out[M,N] = epilogue(A[M,K] @ B[N,K]^T).  a_t / b_t: the operand is stored transposed ([K,M] / [K,N]).
     A and B are both bf16 or both fp16.  ln_stats / ln_c: LayerNorm of A's rows folded into the epilogue (see the header);
     stats_out: row (sum, sumsq) of an fp16-residual output, accumulated.  colsum_out (DGELU epilogue): fp32 [N], += column sums
     of the output over its M rows (the bias gradient of the Linear whose pre-activation is aux_in).
     group: dict(rows=, K=, a_k=0, a_m=0, b_k=0, b_n=0, bias=0) — a grouped GEMM (see ub_gemm_epilogue.group_*): `out` stacks the
     groups' outputs along M, K is the per-group contraction length and the operands are addressed with the group offsets.
+    act=UB_ACT_DOT_AUX with aux_in, dot_out (fp32 [M // dot_seq_len, N // 64, dot_seq_len]) and dot_seq_len: besides C, the per-(row,
+    64-column head) dot product of the bf16 output with aux_in (D = rowsum(dO o O) for the attention backward, from the GEMM that
+    produces dO).
     stream_k: hand the library this stream's stream-K scratch, so that a partial last wave of tiles may be cut along K
     (None = the UB_GEMM_SK environment default, off: measured slower on B200, see profiles/gemm_streamk_r02.md)."""
     ab = F16 if a.dtype == F16 else BF16
@@ -164,6 +167,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=
         if colsum_out.numel() != N:
             raise _cabi.UBError("gemm: colsum_out must be fp32 [N]")
         ep.colsum_out = _p(colsum_out, F32, "colsum_out")
+    if dot_out is not None:
+        if act != UB_ACT_DOT_AUX or aux_in is None or dot_seq_len <= 0 or M % dot_seq_len or N % 64 or dot_out.numel() != M * (N // 64):
+            raise _cabi.UBError("gemm: dot_out needs act=UB_ACT_DOT_AUX, aux_in, dot_seq_len dividing M and fp32 [M / S, N / 64, S]")
+        ep.dot_out, ep.dot_seq_len = _p(dot_out, F32, "dot_out"), int(dot_seq_len)
     if stream_k is None:
         stream_k = _SK_DEFAULT
     if stream_k and split_k == 1 and group is None and M > 256 and N > 128:
@@ -203,6 +210,8 @@ def attn_bwd(qkv, o, d_o, lse, d_ws, dqkv, n_seq, S, H, scale, dbias=None):
     if S <= 320:
         global LAUNCHES
         LAUNCHES -= 1          # D pre-pass + ONE backward kernel for resident items; longer sequences run the dK/dV and dQ passes
+    if o is None:
+        LAUNCHES -= 1          # D was written by the GEMM that produced d_o (gemm(..., act=UB_ACT_DOT_AUX, dot_out=d_ws)): no prep kernel
     check(lib.ub_attn_bwd(_p(qkv, BF16, "qkv"), _p(o, BF16, "o"), _p(d_o, BF16, "d_o"), _p(lse, F32, "lse"),
                           _p(d_ws, F32, "D_ws"), _p(dqkv, BF16, "dqkv"), _p(dbias, F32, "dbias"), n_seq, S, H, scale, _stream()), "ub_attn_bwd")
 

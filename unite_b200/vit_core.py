@@ -51,6 +51,9 @@ _FUSE_QKV_BIAS = os.environ.get("UB_FUSE_QKV_BIAS", "1") == "1"
 # of the block's backward (ub_gemm_wgrad_multi) instead of four: one prologue / pipeline fill / drain and one wave quantisation
 # on the 74 CTA pairs (108 pair tiles x split-K 2 = 216 items = 2.9 waves) instead of four.  UB_MULTI_WGRAD=0: separate launches.
 _MULTI_WGRAD = os.environ.get("UB_MULTI_WGRAD", "1") == "1"
+# D = rowsum(dO o O) of the attention backward from the epilogue of the GEMM that produces dO (ub_gemm_epilogue.dot_out) instead of
+# a separate pass over O and dO per layer.  UB_FUSE_DPREP=0: separate pre-pass inside ub_attn_bwd.
+_FUSE_DPREP = os.environ.get("UB_FUSE_DPREP", "1") == "1"
 _FORCE_WGRAD_SPLIT = int(os.environ.get("UB_WGRAD_SPLIT", "0"))      # experiments: fixed split-K factor of the multi-problem launch
 
 
@@ -330,11 +333,16 @@ class ViTTrunk:
             ops.layernorm_bwd(ws.d_h, L.x_mid, self.p(b + "norm2.weight"), self.eps, ws.dx, ws.dx, dxs_a, s_att, N,
                               self.g(b + "norm2.weight"), self.g(b + "norm2.bias"), dsum=self.g(b + "attn.proj.bias"))
             # ---- attention branch: x_mid = x_in + s * (attn(h1) Wp^T + bp)
-            ops.gemm(dxs_a, self.w(b + "attn.proj.weight"), ws.d_o, b_t=True)
+            if _FUSE_DPREP:
+                # the proj dgrad GEMM that produces dO also leaves D = rowsum(dO o O) per (token, head) for the attention backward
+                ops.gemm(dxs_a, self.w(b + "attn.proj.weight"), ws.d_o, b_t=True, act=ops.UB_ACT_DOT_AUX, aux_in=L.o, dot_out=ws.d_ws,
+                         dot_seq_len=N)
+            else:
+                ops.gemm(dxs_a, self.w(b + "attn.proj.weight"), ws.d_o, b_t=True)
             wgrad(dxs_a, L.o, self.g(b + "attn.proj.weight"))
             # q_bias | (always-zero k gap) | v_bias are one contiguous 3D span of the gradient arena; the attention backward adds the
             # column sums of dq and dv into it as it stores them (the key bias is structurally zero, modeling_finetune.py:104)
-            ops.attn_bwd(L.qkv, L.o, ws.d_o, L.lse, ws.d_ws, dqkv, ws.B, N, self.H, self.scale,
+            ops.attn_bwd(L.qkv, None if _FUSE_DPREP else L.o, ws.d_o, L.lse, ws.d_ws, dqkv, ws.B, N, self.H, self.scale,
                          dbias=self.qkv_bias_grad(l) if _FUSE_QKV_BIAS else None)
             ops.gemm(dqkv, self.w(b + "attn.qkv.weight"), ws.d_h, b_t=True)
             wgrad(dqkv, L.h1, self.g(b + "attn.qkv.weight"))
