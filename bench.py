@@ -508,7 +508,9 @@ def main():
         total_ms = sum(v[1] for v in by.values())
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
         traffic, traffic_src = None, None
-        tp = os.path.join(ROOT, "profiles", "ncu_step_dram_r02.json")
+        tp = os.path.join(ROOT, "profiles", "ncu_step_dram_r02_final.json")          # capture of the final build's launch set
+        if not os.path.exists(tp):
+            tp = os.path.join(ROOT, "profiles", "ncu_step_dram_r02.json")
         if os.path.exists(tp):
             td = json.load(open(tp))
             fam = td.get("families", {}).get("gemm")

@@ -8,7 +8,7 @@ import re
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-FAMILIES = [("gemm", r"gemm_kernel"), ("attn_teacher_fwd", r"attn_fwd_tc_kernel"), ("attn_student_fwd", r"attn_fwd_lse"),
+FAMILIES = [("gemm", r"gemm_kernel|gemm_multi_kernel"), ("attn_teacher_fwd", r"attn_fwd_tc_kernel"), ("attn_student_fwd", r"attn_fwd_lse"),
             ("attn_student_bwd", r"attn_bwd"), ("attn_mma_sync", r"flash_"), ("cls_attn", r"cls_attn"),
             ("layernorm_fwd", r"layernorm_fwd|ln_fwd"), ("layernorm_bwd", r"layernorm_bwd|ln_bwd"), ("teacher_embed_ln", r"teacher_embed"),
             ("dec_tail_fwd", r"dec_tail_fwd"), ("dec_tail_bwd", r"dec_tail_bwd"), ("l2norm_rows", r"l2norm"), ("patchify", r"patchify"),
