@@ -84,7 +84,9 @@ typedef struct ub_gemm_epilogue {
    * workspace the cost model still decides per call whether the split is taken.  Measured on B200 (profiles/gemm_streamk_r02.md):
    * bit-reproducible and within fp32 rounding of the whole-tile schedule, but 2-4 % SLOWER on the step's shapes — the partial
    * last wave is not what bounds them (the pairs that remain active get the idle pairs' share of the L2 -> SM path) — so the
-   * Python front end passes a workspace only on request (ops.gemm(stream_k=True) / UB_GEMM_SK=1). */
+   * Python front end passes a workspace only on request (ops.gemm(stream_k=True) / UB_GEMM_SK=1), and the default library is built
+   * WITHOUT the schedule (ub_gemm_sk_compiled() == 0: the field is ignored); -DUB_GEMM_STREAMK (libunite_b200_sk.so, loaded with
+   * UB_LIB_VARIANT=sk) compiles it in. */
   void* sk_workspace;
   int64_t sk_workspace_bytes;
   /* UB_ACT_DOT_AUX (bf16 out, N a multiple of 64): C = acc as usual, and in the same pass
@@ -99,6 +101,9 @@ typedef struct ub_gemm_epilogue {
 
 /* bytes of ub_gemm_epilogue.sk_workspace that cover every shape on this device */
 UB_API int64_t ub_gemm_sk_workspace_bytes(void);
+/* 1 if this build of the library contains the stream-K tail (-DUB_GEMM_STREAMK: libunite_b200_sk.so), 0 if sk_workspace is ignored
+ * (the default build: the schedule's bookkeeping costs the ordinary path 0.9 % of the step and no shape gains from it on B200) */
+UB_API int ub_gemm_sk_compiled(void);
 /* diagnostic: how many ub_gemm_bf16 calls of this process took the stream-K tail schedule */
 UB_API int64_t ub_gemm_sk_launches(void);
 /* Diagnostic (host only, no GPU needed): the stream-K plan the kernel follows for T tiles of KB k-blocks on U CTA pairs with a

@@ -1,6 +1,7 @@
 """Stream-K tail of the GEMM: parity (split vs whole-tile schedule vs fp32 torch) over every epilogue the step uses, ragged shapes,
 repeated launches (the counters must return to zero), and per-shape timing with a flushed L2.
-    python tools/gemm_sk_check.py [--time]        (run under gpurun; writes gpurun_out/gemm_sk_check.json)"""
+    UB_LIB_VARIANT=sk python tools/gemm_sk_check.py [--time | --quick]        (run under gpurun; writes gpurun_out/gemm_sk_check.json)
+The schedule is a build option (-DUB_GEMM_STREAMK -> libunite_b200_sk.so, built by __graft_entry__.build())."""
 import json
 import os
 import sys
@@ -108,7 +109,20 @@ def case(kind, M, N, K, time_it=False, name=""):
     return ok
 
 
+QUICK = (("res32", 10240, 768, 3072), ("nn", 10240, 768, 2304), ("gelu_aux", 10240, 3072, 768), ("dgelu", 10240, 3072, 768),
+         ("res32", 10100, 776, 3000), ("res16", 10240, 768, 3072), ("acc32", 4096, 1024, 4096), ("nn", 20480, 1024, 1024),
+         ("plain", 3200, 768, 1024))
+
 if __name__ == "__main__":
+    if not _cabi.lib.ub_gemm_sk_compiled():
+        print("this build of the library has no stream-K tail (default build): run with UB_LIB_VARIANT=sk")
+        sys.exit(2)
+    if "--quick" in sys.argv:            # the pytest subset: every epilogue, ragged shapes, >= 8 of 9 cases must really split
+        ok = all([case(*c) for c in QUICK])
+        n_split = sum(r["split"] for r in results)
+        print(f"{n_split} of {len(results)} cases took the split")
+        print("ALL OK" if ok and n_split >= 8 else "FAILURES", flush=True)
+        sys.exit(0 if ok and n_split >= 8 else 1)
     timing = "--time" in sys.argv
     ok = True
     # the step's shapes (B = 32: M = 10 240), every epilogue that can meet a split tail

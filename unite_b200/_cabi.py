@@ -75,6 +75,7 @@ SIGNATURES = {
     "ub_set_sm_limit": (C.c_int, [_I]),
     "ub_gemm_cluster4_capacity": (C.c_int, []),
     "ub_gemm_sk_workspace_bytes": (C.c_int64, []),
+    "ub_gemm_sk_compiled": (C.c_int, []),
     "ub_gemm_sk_launches": (C.c_int64, []),
     "ub_gemm_sk_schedule": (C.c_int, [_I, _I, _I, _I, _I, C.POINTER(C.c_int32)]),
     "ub_gemm_bf16": (C.c_int, [_P, _L, _I, _P, _L, _I, _P, _L, _I, _I, _I, C.POINTER(GemmEpilogue), _I, _P]),

@@ -233,7 +233,14 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   // [partial piece] [its whole tiles] [finishing piece]: partial accumulators (fp32, parked in the workspace by the epilogue warps
   // and announced through a per-(tile, CTA, warp) counter) are written at the start of the kernel and consumed at its end, so the
   // wait is off the critical path and cannot form a cycle (a partial piece waits for nothing).
+  // The stream-K tail is a BUILD option (-DUB_GEMM_STREAMK, libunite_b200_sk.so): compiled in, its item bookkeeping costs the ordinary
+  // whole-tile schedule 0.9 % of the step (17.385 vs 17.536 ms, A/B/A/B/A/B, profiles/ab_streamk_scaffolding_r02.txt) — more than any
+  // shape gains from it on B200 (profiles/gemm_streamk_r02.md) — so the default library is built without it.
+#ifdef UB_GEMM_STREAMK
   constexpr bool SK_OK = NCTA == 2 && BN == 256 && !MULTI;
+#else
+  constexpr bool SK_OK = false;
+#endif
   const bool sk = SK_OK && p.sk_tiles > 0;
   int n_items, n_dp = 0;
   int part_tile = -1, part_kb0 = 0, part_kb1 = 0, part_slot = 0;      // this pair's partial piece (at most one)
@@ -928,6 +935,13 @@ static int launch_gemm(const GemmMaps& m, const GemmParams& p, int epi, bool out
 
 extern "C" int ub_gemm_cluster4_capacity(void) { return ub::max_clusters4(); }
 extern "C" int64_t ub_gemm_sk_launches(void) { return ub::g_sk_launches; }
+extern "C" int ub_gemm_sk_compiled(void) {
+#ifdef UB_GEMM_STREAMK
+  return 1;
+#else
+  return 0;
+#endif
+}
 // test hook: the stream-K plan for T tiles on U pairs with KB k-blocks per tile and pair u's share of it, as the kernel computes them
 // out = {first, tiles, units, n_dp, part_tile, part_kb0, part_kb1, part_slot, fin_tile, fin_kb0, fin_wait}; returns 1 if the tail is split
 extern "C" int ub_gemm_sk_schedule(int T, int U, int KB, int overhead, int u, int32_t* out) {
@@ -1147,6 +1161,7 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
     sk_overhead = o ? atoi(o) : 4;
     if (sk_overhead < 0) sk_overhead = 0;
   }
+#ifdef UB_GEMM_STREAMK
   if (ep.sk_workspace != nullptr && ncta == 2 && bn == 256 && split_k == 1 && ep.group_rows == 0 && ep.max_ctas >= 0 &&
       total_work > 0 && total_work < (1l << 30)) {
     const SkPlan pl = sk_plan((int)total_work, units, total_kb, sk_overhead);
@@ -1157,6 +1172,9 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
       ++g_sk_launches;
     }
   }
+#else
+  (void)sk_overhead;
+#endif
   int grid = (int)(total_work < units ? total_work : units) * ncta;
   if (p.sk_tiles > 0) grid = (p.sk_first > 0 ? units : p.sk_units) * ncta;      // every pair of the split takes part
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
