@@ -40,7 +40,7 @@ constexpr int GEMM_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogu
 #endif
 template <int BN, int EPI, int NCTA>
 struct GemmCfg {
-  static constexpr int NBUF = (EPI != 0 && !(BN == 256 && NCTA == 1)) ? UB_GEMM_EPI_NBUF : 2;
+  static constexpr int NBUF = (EPI != 0 && EPI != 4 && !(BN == 256 && NCTA == 1)) ? UB_GEMM_EPI_NBUF : 2;
   static constexpr int EPI_BYTES = 8 * NBUF * 4096;      // 8 epilogue warps x NBUF staging slabs
   static constexpr int stages(int requested) { return NBUF == 3 && requested > 4 ? 4 : requested; }
 };
@@ -132,7 +132,8 @@ struct GemmMultiMaps {
 };
 
 // EPI : 0 = bias / activation (/ pre-activation copy), 1 = + fp32 residual (fp32 out), 2 = DGELU: * gelu'(aux) (bf16 out),
-//       3 = + fp16 residual (fp16 out: the frozen teacher's residual stream)
+//       3 = + fp16 residual (fp16 out: the frozen teacher's residual stream), 4 = EPI 0 with the LayerNorm fold (its own
+//       instantiation: the fold's column sums are 32 registers that the plain epilogues should not carry)
 // OUT32: C is fp32 (32-column slabs) or bf16 (64-column slabs); both give 128-byte staging rows
 // NCTA: 1 = one CTA per 128 x BN tile; 2 = CTA pair per 256 x BN tile; 4 = cluster of two pairs on a 512 x BN tile that
 //       share B: each CTA fetches a quarter of the B tile and TMA-multicasts it to the CTA of the same rank in the other pair
@@ -410,7 +411,7 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
       return tn * BN + half * (BN / 2) + c * CW;
     };
     // the partial piece of a stream-K tail comes first and uses neither the staging slabs nor the operand prefetch chain
-    if (EPI != 0 && n_part < n_items && lane == 0) {
+    if (EPI != 0 && EPI != 4 && n_part < n_items && lane == 0) {
       // residual / pre-activation slabs of the first NBUF - 1 (tile, slab) pairs of this warp
       mbar_expect_tx(&rb[0], 4096);
       tma_load_2d(&tmR, &rb[0], slab0, slab_col(n_part, 0), slab_row(n_part));
@@ -476,7 +477,7 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
         rscale = row < p.M ? __ldg(p.row_scale + row / p.rows_per_scale) : 0.0f;
       }
       float ln_rstd = 1.0f, ln_rm = 0.0f;       // LayerNorm fold: acc -> rstd * acc - (rstd * mu) * c[n]
-      if (EPI == 0 && p.ln_stats != nullptr) {
+      if (EPI == 4) {
         const int row = row0 + lane;
         if (row < p.M) {
           const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + row);
@@ -530,7 +531,7 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
         const int b = NBUF == 3 ? (int)(cc % 3u) : (int)(cc & 1u);
         const int col0 = slab_col(w, c);
         // ---- staging-buffer hand-over with the TMA engine
-        if (EPI == 0) {
+        if (EPI == 0 || EPI == 4) {
           // buffer b was last read by the store issued two slabs ago (one slab ago when a pre-activation copy uses b^1)
           if (lane == 0) {
             if (p.has_aux_out) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
@@ -560,12 +561,12 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
           tmem_ld_32x32(t_row + (uint32_t)(c * CW + h * 32), r);
           // LayerNorm fold: the column sums of B for these 32 columns are fetched (L1-resident, same address for every lane)
           // while the accumulator load is in flight
-          float4 cc[EPI == 0 ? 8 : 1];
-          if (EPI == 0 && p.ln_stats != nullptr) {
+          float4 cc[EPI == 4 ? 8 : 1];
+          if (EPI == 4) {
             const int gc = col0 + h * 32;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              cc[EPI == 0 ? j : 0] = (gc + 4 * j < p.N) ? __ldg(reinterpret_cast<const float4*>(p.ln_c + gc + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              cc[EPI == 4 ? j : 0] = (gc + 4 * j < p.N) ? __ldg(reinterpret_cast<const float4*>(p.ln_c + gc + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           tmem_ld_wait();
           float v[32];
@@ -579,11 +580,11 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
             const int blk = c * (CW / 32) + h + 1;
             if (blk < (BN / 2) / 32) sk_fetch(blk);
           }
-          if (EPI == 0 && p.ln_stats != nullptr) {
+          if (EPI == 4) {
             const float2 rs2 = make_float2(ln_rstd, ln_rstd), nrm2 = make_float2(-ln_rm, -ln_rm);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 q = cc[EPI == 0 ? j : 0];
+              const float4 q = cc[EPI == 4 ? j : 0];
               const float2 a = __ffma2_rn(nrm2, make_float2(q.x, q.y), __fmul2_rn(rs2, make_float2(v[4 * j], v[4 * j + 1])));
               const float2 b = __ffma2_rn(nrm2, make_float2(q.z, q.w), __fmul2_rn(rs2, make_float2(v[4 * j + 2], v[4 * j + 3])));
               v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = b.x; v[4 * j + 3] = b.y;
@@ -597,7 +598,7 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
               v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
             }
           }
-          if (EPI == 0) {
+          if (EPI == 0 || EPI == 4) {
             if (p.act == UB_ACT_QUICKGELU) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
@@ -736,7 +737,7 @@ UB_DEVINL void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
         if (lane == 0) {
           if (p.accumulate) tma_reduce_add_2d(pC, slab0 + (b << 12), col0, row0);
           else tma_store_2d(pC, slab0 + (b << 12), col0, row0);
-          if (EPI == 0 && p.has_aux_out) tma_store_2d(&tmX, slab0 + ((b ^ 1) << 12), col0, row0);
+          if ((EPI == 0 || EPI == 4) && p.has_aux_out) tma_store_2d(&tmX, slab0 + ((b ^ 1) << 12), col0, row0);
           tma_store_commit();
         }
       }
@@ -922,6 +923,7 @@ static int launch_gemm(const GemmMaps& m, const GemmParams& p, int epi, bool out
   } else {
     if (epi == 0 && out32) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 0, true, NCTA>(m, p, grid, stream);
     if (epi == 0 && !out32) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 0, false, NCTA>(m, p, grid, stream);
+    if (epi == 4 && !out32) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 4, false, NCTA>(m, p, grid, stream);
     if (epi == 1) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 1, true, NCTA>(m, p, grid, stream);
     if (epi == 2) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 2, false, NCTA>(m, p, grid, stream);
     if (epi == 3) return launch_gemm_epi<BN, STAGES, A_MN, B_MN, 3, false, NCTA>(m, p, grid, stream);
@@ -1039,8 +1041,9 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   UB_REQUIRE(ep.residual == nullptr || ep.out_fp32 || ep.residual_f16, "gemm: the residual epilogue writes fp32 (or fp16 with residual_f16)");
   UB_REQUIRE(!ep.residual_f16 || (ep.residual != nullptr && !ep.out_fp32), "gemm: residual_f16 needs a residual and a 2-byte (fp16) output");
   UB_REQUIRE((ep.ln_stats == nullptr) == (ep.ln_c == nullptr), "gemm: ln_stats and ln_c go together");
-  UB_REQUIRE(ep.ln_stats == nullptr || (ep.residual == nullptr && ep.act != UB_ACT_DGELU && !ep.accumulate && ep.ln_inv_d > 0.f && N % 4 == 0),
-             "gemm: the LayerNorm fold works with the bias / activation epilogue only");
+  UB_REQUIRE(ep.ln_stats == nullptr || (ep.residual == nullptr && ep.act != UB_ACT_DGELU && ep.act != UB_ACT_DOT_AUX && !ep.accumulate &&
+                                        ep.ln_inv_d > 0.f && N % 4 == 0 && !ep.out_fp32 && !a_mn_major && !b_mn_major),
+             "gemm: the LayerNorm fold works with the bias / activation epilogue, K-major operands and a 2-byte output only");
   UB_REQUIRE(ep.stats_out == nullptr || ep.residual_f16, "gemm: stats_out belongs to the fp16-residual epilogue");
   UB_REQUIRE(ep.act != UB_ACT_DGELU || !ep.out_fp32, "gemm: the DGELU epilogue writes bf16");
   UB_REQUIRE(ep.colsum_out == nullptr || ep.act == UB_ACT_DGELU, "gemm: colsum_out belongs to the DGELU epilogue");
@@ -1109,7 +1112,8 @@ extern "C" int ub_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const vo
   if (ep.tile_ctas == 2 && bn == 256 && M > BM) ncta = 2;
   if (ep.tile_ctas == 4 && bn == 256 && M >= 4 * BM && units4 > 0) ncta = 4;
 
-  const int epi = ep.residual != nullptr ? (ep.residual_f16 ? 3 : 1) : ((ep.act == UB_ACT_DGELU || ep.act == UB_ACT_DOT_AUX) ? 2 : 0);
+  const int epi = ep.residual != nullptr ? (ep.residual_f16 ? 3 : 1)
+                                         : ((ep.act == UB_ACT_DGELU || ep.act == UB_ACT_DOT_AUX) ? 2 : (ep.ln_stats != nullptr ? 4 : 0));
   const bool out32 = ep.out_fp32 != 0;
   GemmMaps m;
   memset(&m, 0, sizeof(m));
