@@ -76,6 +76,7 @@ def _p2d(t: torch.Tensor, dtype, what):
 # being captured lives in that graph's pool and stays alive here.
 _SK_WS = {}
 _SK_DEFAULT = os.environ.get("UB_GEMM_SK", "0") not in ("", "0")
+_SK_COMPILED = bool(lib.ub_gemm_sk_compiled())      # only libunite_b200_sk.so (UB_LIB_VARIANT=sk) contains the schedule
 
 
 def _sk_workspace(ep):
@@ -173,7 +174,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_t=False, b_t=
         ep.dot_out, ep.dot_seq_len = _p(dot_out, F32, "dot_out"), int(dot_seq_len)
     if stream_k is None:
         stream_k = _SK_DEFAULT
-    if stream_k and split_k == 1 and group is None and M > 256 and N > 128:
+    if stream_k and _SK_COMPILED and split_k == 1 and group is None and M > 256 and N > 128:
         _sk_workspace(ep)
     check(lib.ub_gemm_bf16(pa, lda, int(a_t), pb, ldb, int(b_t), pc, ldc, M, N, K, C.byref(ep), split_k, _stream()), "ub_gemm_bf16")
     return out
